@@ -1,0 +1,1039 @@
+// Host side of the C ABI (include/ghostm_b200.h): device buffers, stage orchestration, the
+// extended gm_* entry points and the ten legacy symbols of the reference's aligner_gpu.h.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "gm_common.cuh"
+
+namespace gm {
+
+// ---- kernels defined in the other translation units -----------------------------------
+int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips);
+cudaError_t sw_extend_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream);
+cudaError_t sw_extend_s32_launch(const SwParams &p, int sm_count, cudaStream_t stream);
+uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions);
+cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream);
+int search_max_list_len();
+int search_max_threshold();
+size_t merge_smem_bytes(uint32_t elems_per_warp);
+cudaError_t merge_launch(const MergeParams &p, int sm_count, cudaStream_t stream);
+int traceback_grid(int sm_count);
+int traceback_threads();
+cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_t stream);
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(gm_status st, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return (int)st;
+}
+
+#define GM_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(GM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                   \
+  } while (0)
+
+// ---- small utility kernels --------------------------------------------------------------
+
+// out[i] = exclusive prefix over i of f(in[first + i]); out[n] = total.  One CTA.
+// mode 0: f(x) = x      mode 1: f(x) = ceil(x / 64)   (SW tasks per query)
+__global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *in, uint32_t first, uint32_t n,
+                                                    uint32_t *out, int mode) {
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t carry;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + tid;
+    uint32_t v = 0;
+    if (i < n) {
+      v = in[first + i];
+      if (mode == 1) v = (v + kSwCandPerTask - 1) / kSwCandPerTask;
+    }
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t before = carry;
+    for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
+    if (i < n) out[i] = before + incl - v;
+    __syncthreads();
+    if (tid == 1023) carry = before + incl;
+    __syncthreads();
+  }
+  if (tid == 0) out[n] = carry;
+}
+
+// Copy per-query candidate slices into reference order (queries ascending).
+__global__ void gather_kernel(const uint32_t *cand_off, const uint32_t *cand_cnt,
+                              const uint32_t *prefix, uint32_t first, uint32_t n_q,
+                              const uint32_t *src0, const uint32_t *src1, uint32_t *dst0,
+                              uint32_t *dst1, uint32_t *dst_query) {
+  for (uint32_t qi = blockIdx.x; qi < n_q; qi += gridDim.x) {
+    const uint32_t q = first + qi, off = cand_off[q], cnt = cand_cnt[q], o = prefix[qi];
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      if (dst0) dst0[o + i] = src0[off + i];
+      if (dst1) dst1[o + i] = src1[off + i];
+      if (dst_query) dst_query[o + i] = q;
+    }
+  }
+}
+
+// db_creator.cpp:167-241 on the device: key of every indexable position (or 0xFFFFFFFF).
+__global__ void index_keys_kernel(const uint8_t *seq, uint32_t seq_len, const uint32_t *seq_starts,
+                                  uint32_t n_seqs, uint32_t seed, uint32_t seed_len, uint32_t *keys,
+                                  uint32_t *pos) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < seq_len;
+       j += gridDim.x * blockDim.x) {
+    uint32_t key = 0;
+    bool ok = j + seed_len <= seq_len;
+    uint32_t s = seed;
+    for (uint32_t i = 0; ok && s != 0; ++i, s >>= 1) {
+      const uint8_t c = seq[j + i];
+      if (c == kSeqEnd || c == kBaseX) ok = false;        // :198 loop bound, :201-212
+      if (s & 1) key = (key << kCharBits) | c;
+    }
+    if (ok) {
+      // :197 only sequences strictly longer than the seed span are indexed
+      uint32_t lo = 0, hi = n_seqs;  // largest id with seq_starts[id] <= j
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seq_starts[mid] <= j) lo = mid; else hi = mid;
+      }
+      const uint32_t end = (lo + 1 < n_seqs) ? seq_starts[lo + 1] : seq_len;
+      if (end - seq_starts[lo] - 1 <= seed_len) ok = false;
+    }
+    keys[j] = ok ? key : 0xFFFFFFFFu;
+    pos[j] = j;
+  }
+}
+
+__global__ void index_bounds_kernel(const uint32_t *sorted_keys, uint32_t n, uint32_t n_keys,
+                                    uint32_t *keys_count) {
+  // keys_count[k] = first index i with sorted_keys[i] >= k  (exclusive prefix sums)
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k <= n_keys;
+       k += gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (sorted_keys[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    keys_count[k] = lo;
+  }
+}
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(want, 1) * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct DbChunk {
+  DevBuf<uint8_t> seq;
+  DevBuf<uint32_t> keys_count, positions, seq_starts;
+  uint32_t seq_len = 0, keys_count_len = 0, positions_len = 0, n_seqs = 0;
+  bool valid = false;
+};
+
+}  // namespace
+}  // namespace gm
+
+using namespace gm;
+
+struct gm_context {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {};
+
+  bool has_opt = false;
+  gm_options opt = {};
+  uint32_t seed_len = 0, list_len = 0;
+  bool use_s32 = false;
+  DevBuf<int32_t> matrix;
+
+  DbChunk chunks[GM_MAX_DB_CHUNKS];
+  int cur_chunk = -1;   // chunk the resident candidates belong to
+
+  // queries
+  DevBuf<uint8_t> queries;
+  uint32_t n_queries = 0, query_len = 0;
+  DevBuf<uint32_t> run_first, run_last;
+  uint32_t n_runs = 0;
+
+  // candidates of (resident queries x cur_chunk)
+  uint64_t cand_capacity = 1ull << 26;
+  DevBuf<uint32_t> cand_off, cand_cnt, cand_start, cand_score, cand_end;
+  DevBuf<uint32_t> staging;
+  uint32_t staging_cap = 1u << 15;
+  DevBuf<uint32_t> prefix;            // scan output (n_queries + 1)
+  DevBuf<uint32_t> gather0, gather1, gather2;
+  DevBuf<uint32_t> strip_scratch;
+  DevBuf<unsigned long long> counters;  // [0] cand cursor [1] positions visited [2] cells [3] big cursor
+  DevBuf<uint32_t> small;               // [0] query counter [1] task counter [2] overflow [3] n_jobs
+                                        // [4] merge error [5] run counter
+  uint64_t cand_total = 0;
+  std::vector<uint32_t> h_counts;
+
+  // hit lists
+  DevBuf<gm_hit> hits[2];
+  DevBuf<uint32_t> hit_cnt[2];
+  int cur_hits = 0;
+  uint32_t cap = 1;
+  DevBuf<uint32_t> jobs;
+  DevBuf<unsigned long long> big_scratch;
+  DevBuf<int> tb_work;
+};
+
+namespace {
+
+int check_ctx(gm_context *ctx) {
+  if (!ctx) return fail(GM_ERR_ARGUMENT, "null context");
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return fail(GM_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+  return 0;
+}
+
+uint32_t seed_length_of(uint32_t seed) {  // index.h:137-147
+  uint32_t n = 0;
+  for (; seed; seed >>= 1) ++n;
+  return n;
+}
+
+int ensure_query_state(gm_context *c) {
+  if (!c->has_opt) return fail(GM_ERR_ARGUMENT, "gm_set_options must be called first");
+  if (c->n_queries == 0) return fail(GM_ERR_ARGUMENT, "no queries resident (gm_query_upload)");
+  return 0;
+}
+
+int derive_query_options(gm_context *c) {
+  // called when both options and queries are known
+  if (c->query_len < c->seed_len) return fail(GM_ERR_ARGUMENT, "query shorter than the seed");
+  if (c->opt.shift == 0) return fail(GM_ERR_ARGUMENT, "shift must be > 0");
+  c->list_len = (c->query_len - c->seed_len) / c->opt.shift + 1;  // aligner.cpp:399
+  if (c->list_len > (uint32_t)search_max_list_len())
+    return fail(GM_ERR_UNSUPPORTED, "list length %u exceeds %d", c->list_len, search_max_list_len());
+  // packed s16 range check for the DPX kernel: every intermediate stays inside
+  // [-16384 + open, L * max_score]; fall back to the 32-bit kernel otherwise.
+  int hi = 0, lo = 0;
+  for (int i = 0; i < 1024; ++i) {
+    hi = std::max(hi, c->opt.score_matrix[i]);
+    lo = std::min(lo, c->opt.score_matrix[i]);
+  }
+  const long max_score = (long)c->query_len * hi;
+  c->use_s32 = max_score - c->opt.open_gap > 16000 || lo - c->opt.open_gap < -16000 ||
+               c->opt.open_gap < -4000 || c->opt.extend_gap < -4000 || c->opt.open_gap > 0 ||
+               c->opt.extend_gap > 0;
+  if (c->use_s32 && c->query_len > 1024)
+    return fail(GM_ERR_UNSUPPORTED, "score range needs the 32-bit kernel, which is limited to L <= 1024");
+  return 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+// extended API
+// =========================================================================================
+
+extern "C" const char *gm_version(void) { return "ghostm_b200 0.1 (sm_100a)"; }
+extern "C" const char *gm_last_error(void) { return g_error.c_str(); }
+
+extern "C" int gm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int gm_create(int device, gm_context **out) {
+  if (!out) return fail(GM_ERR_ARGUMENT, "null out pointer");
+  *out = nullptr;
+  GM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(GM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  gm_context *c = new gm_context();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  GM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto &e : c->ev) GM_CUDA(cudaEventCreate(&e));
+  GM_CUDA(c->counters.ensure(8));
+  GM_CUDA(c->small.ensure(8));
+  GM_CUDA(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+  GM_CUDA(cudaMemsetAsync(c->small.p, 0, 8 * sizeof(uint32_t), c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+extern "C" void gm_destroy(gm_context *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto &ch : c->chunks) {
+    ch.seq.release(); ch.keys_count.release(); ch.positions.release(); ch.seq_starts.release();
+  }
+  c->matrix.release(); c->queries.release(); c->run_first.release(); c->run_last.release();
+  c->cand_off.release(); c->cand_cnt.release(); c->cand_start.release(); c->cand_score.release();
+  c->cand_end.release(); c->staging.release(); c->prefix.release(); c->gather0.release();
+  c->gather1.release(); c->gather2.release(); c->strip_scratch.release(); c->counters.release();
+  c->small.release(); c->hits[0].release(); c->hits[1].release(); c->hit_cnt[0].release();
+  c->hit_cnt[1].release(); c->jobs.release(); c->big_scratch.release(); c->tb_work.release();
+  for (auto &e : c->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int gm_set_options(gm_context *c, const gm_options *opt) {
+  if (int r = check_ctx(c)) return r;
+  if (!opt) return fail(GM_ERR_ARGUMENT, "null options");
+  if (opt->seed == 0) return fail(GM_ERR_ARGUMENT, "seed mask is 0");
+  if (opt->threshold > (uint32_t)search_max_threshold())
+    return fail(GM_ERR_UNSUPPORTED, "threshold %u > %d is not implemented by the seed-search kernel",
+                opt->threshold, search_max_threshold());
+  if (opt->log_region > 20) return fail(GM_ERR_ARGUMENT, "log_region %u out of range", opt->log_region);
+  c->opt = *opt;
+  c->seed_len = seed_length_of(opt->seed);
+  c->has_opt = true;
+  c->cap = std::max<uint32_t>(opt->best, 1);
+  GM_CUDA(c->matrix.ensure(1024));
+  GM_CUDA(cudaMemcpyAsync(c->matrix.p, opt->score_matrix, 1024 * sizeof(int32_t),
+                          cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->n_queries) {
+    for (int b = 0; b < 2; ++b)
+      if (c->hits[b].n < (size_t)c->n_queries * c->cap) {
+        GM_CUDA(c->hits[0].ensure((size_t)c->n_queries * c->cap));
+        GM_CUDA(c->hits[1].ensure((size_t)c->n_queries * c->cap));
+        GM_CUDA(c->jobs.ensure((size_t)c->n_queries * c->cap));
+        GM_CUDA(cudaMemset(c->hit_cnt[0].p, 0, (size_t)c->n_queries * 4));
+        GM_CUDA(cudaMemset(c->hit_cnt[1].p, 0, (size_t)c->n_queries * 4));
+        break;
+      }
+    return derive_query_options(c);
+  }
+  return 0;
+}
+
+extern "C" int gm_set_candidate_capacity(gm_context *c, uint64_t n) {
+  if (int r = check_ctx(c)) return r;
+  if (n == 0 || n >= (1ull << 32)) return fail(GM_ERR_ARGUMENT, "capacity must be in [1, 2^32)");
+  c->cand_capacity = n;
+  return 0;
+}
+
+extern "C" int gm_db_upload(gm_context *c, uint32_t id, const uint8_t *seq, uint32_t seq_len,
+                            const uint32_t *keys_count, uint32_t keys_count_len,
+                            const uint32_t *positions, uint32_t positions_len,
+                            const uint32_t *seq_starts, uint32_t n_seqs) {
+  if (int r = check_ctx(c)) return r;
+  if (id >= GM_MAX_DB_CHUNKS) return fail(GM_ERR_ARGUMENT, "chunk id %u out of range", id);
+  if (!seq || !keys_count || (!positions && positions_len) || !seq_starts || n_seqs == 0)
+    return fail(GM_ERR_ARGUMENT, "null db arrays");
+  DbChunk &ch = c->chunks[id];
+  ch.valid = false;
+  GM_CUDA(ch.seq.ensure(seq_len));
+  GM_CUDA(ch.keys_count.ensure(keys_count_len));
+  GM_CUDA(ch.positions.ensure(positions_len));
+  GM_CUDA(ch.seq_starts.ensure(n_seqs));
+  GM_CUDA(cudaMemcpyAsync(ch.seq.p, seq, seq_len, cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(cudaMemcpyAsync(ch.keys_count.p, keys_count, (size_t)keys_count_len * 4,
+                          cudaMemcpyHostToDevice, c->stream));
+  if (positions_len)
+    GM_CUDA(cudaMemcpyAsync(ch.positions.p, positions, (size_t)positions_len * 4,
+                            cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(cudaMemcpyAsync(ch.seq_starts.p, seq_starts, (size_t)n_seqs * 4, cudaMemcpyHostToDevice,
+                          c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  ch.seq_len = seq_len;
+  ch.keys_count_len = keys_count_len;
+  ch.positions_len = positions_len;
+  ch.n_seqs = n_seqs;
+  ch.valid = true;
+  if (c->cur_chunk == (int)id) c->cur_chunk = -1;
+  return 0;
+}
+
+extern "C" int gm_db_release(gm_context *c, uint32_t id) {
+  if (int r = check_ctx(c)) return r;
+  if (id >= GM_MAX_DB_CHUNKS) return fail(GM_ERR_ARGUMENT, "chunk id %u out of range", id);
+  DbChunk &ch = c->chunks[id];
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  ch.seq.release(); ch.keys_count.release(); ch.positions.release(); ch.seq_starts.release();
+  ch.valid = false;
+  if (c->cur_chunk == (int)id) c->cur_chunk = -1;
+  return 0;
+}
+
+extern "C" int gm_query_upload(gm_context *c, const uint8_t *seqs, uint32_t n, uint32_t L,
+                               const uint8_t *name_break) {
+  if (int r = check_ctx(c)) return r;
+  if (!seqs || n == 0 || L == 0) return fail(GM_ERR_ARGUMENT, "empty query chunk");
+  if (!c->has_opt) return fail(GM_ERR_ARGUMENT, "gm_set_options must be called first");
+  c->n_queries = n;
+  c->query_len = L;
+  if (int r = derive_query_options(c)) { c->n_queries = 0; return r; }
+  GM_CUDA(c->queries.ensure((size_t)n * L));
+  GM_CUDA(cudaMemcpyAsync(c->queries.p, seqs, (size_t)n * L, cudaMemcpyHostToDevice, c->stream));
+  // same-name runs (aligner.cpp:697-700)
+  std::vector<uint32_t> first, last;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (i == 0 || !name_break || name_break[i]) {
+      if (i) last.push_back(i - 1);
+      first.push_back(i);
+    }
+  }
+  last.push_back(n - 1);
+  c->n_runs = (uint32_t)first.size();
+  GM_CUDA(c->run_first.ensure(c->n_runs));
+  GM_CUDA(c->run_last.ensure(c->n_runs));
+  GM_CUDA(cudaMemcpyAsync(c->run_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(cudaMemcpyAsync(c->run_last.p, last.data(), last.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(c->cand_off.ensure(n));
+  GM_CUDA(c->cand_cnt.ensure(n));
+  GM_CUDA(c->prefix.ensure((size_t)n + 1));
+  for (int b = 0; b < 2; ++b) {
+    GM_CUDA(c->hits[b].ensure((size_t)n * c->cap));
+    GM_CUDA(c->hit_cnt[b].ensure(n));
+    GM_CUDA(cudaMemsetAsync(c->hit_cnt[b].p, 0, (size_t)n * 4, c->stream));
+  }
+  GM_CUDA(c->jobs.ensure((size_t)n * c->cap));
+  GM_CUDA(cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)n * 4, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  c->cur_hits = 0;
+  c->cur_chunk = -1;
+  c->cand_total = 0;
+  return 0;
+}
+
+extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t *total,
+                         gm_stats *stats) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  if (id >= GM_MAX_DB_CHUNKS || !c->chunks[id].valid)
+    return fail(GM_ERR_ARGUMENT, "db chunk %u is not resident", id);
+  DbChunk &ch = c->chunks[id];
+  GM_CUDA(c->cand_start.ensure(c->cand_capacity));
+  const int grid = c->sm_count;
+  GM_CUDA(c->staging.ensure((size_t)grid * c->staging_cap));
+  GM_CUDA(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  GM_CUDA(cudaMemsetAsync(c->small.p, 0, 8 * sizeof(uint32_t), c->stream));
+  c->cur_chunk = -1;
+  c->h_counts.assign(c->n_queries, 0);
+
+  if (c->opt.threshold == 0) {
+    // aligner.cpp:416: threshold - 1 wraps to UINT_MAX, `count > threshold` is never true
+    GM_CUDA(cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)c->n_queries * 4, c->stream));
+    GM_CUDA(cudaMemsetAsync(c->cand_off.p, 0, (size_t)c->n_queries * 4, c->stream));
+    GM_CUDA(cudaStreamSynchronize(c->stream));
+  } else {
+    SearchParams p = {};
+    p.queries = c->queries.p;
+    p.query_len = c->query_len;
+    p.n_queries = c->n_queries;
+    p.keys_count = ch.keys_count.p;
+    p.positions = ch.positions.p;
+    p.seed = c->opt.seed;
+    p.seed_len = c->seed_len;
+    p.shift = c->opt.shift;
+    p.log_region = c->opt.log_region;
+    p.threshold = c->opt.threshold;
+    p.list_len = c->list_len;
+    p.n_regions = (ch.seq_len >> c->opt.log_region) + 1;
+    p.tile_regions = search_tile_regions((int)p.threshold, c->smem_optin, p.n_regions);
+    p.cand_off = c->cand_off.p;
+    p.cand_cnt = c->cand_cnt.p;
+    p.cand_start = c->cand_start.p;
+    p.cand_capacity = c->cand_capacity;
+    p.cand_cursor = c->counters.p + 0;
+    p.staging = c->staging.p;
+    p.staging_cap = c->staging_cap;
+    p.query_counter = c->small.p + 0;
+    p.positions_visited = c->counters.p + 1;
+    p.overflow = reinterpret_cast<int *>(c->small.p + 2);
+    GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    GM_CUDA(seed_search_launch(p, grid, c->stream));
+    GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    GM_CUDA(cudaMemcpyAsync(c->h_counts.data(), c->cand_cnt.p, (size_t)c->n_queries * 4,
+                            cudaMemcpyDeviceToHost, c->stream));
+    GM_CUDA(cudaStreamSynchronize(c->stream));
+    int overflow = 0;
+    GM_CUDA(cudaMemcpy(&overflow, c->small.p + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    if (overflow)
+      return fail(GM_ERR_CAPACITY, "candidate buffer (%llu entries) exhausted; raise it with "
+                  "gm_set_candidate_capacity", (unsigned long long)c->cand_capacity);
+    if (stats) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+      stats->ms_search += ms;
+      stats->kernel_launches += 1;
+      unsigned long long v[2];
+      GM_CUDA(cudaMemcpy(v, c->counters.p, sizeof(v), cudaMemcpyDeviceToHost));
+      stats->seed_positions += v[1];
+    }
+  }
+  uint64_t sum = 0;
+  for (uint32_t v : c->h_counts) sum += v;
+  c->cand_total = sum;
+  c->cur_chunk = (int)id;
+  if (counts) memcpy(counts, c->h_counts.data(), (size_t)c->n_queries * 4);
+  if (total) *total = sum;
+  return 0;
+}
+
+extern "C" uint32_t gm_chunk_rule(const uint32_t *counts, uint32_t n, uint32_t first_query,
+                                  uint32_t max_list_length, uint64_t *n_candidates, int *last) {
+  // aligner.cpp:383-389 and :511-519.  first_query == 0 is the first call of a db chunk; any
+  // later chunk starts at the query that overflowed the previous one, whose candidates were
+  // carried over without a budget check.
+  uint64_t count = 0;
+  uint32_t i = first_query;
+  int is_last = 0;
+  uint32_t end = first_query;
+  if (first_query != 0) {
+    if (first_query + 1 >= n) {  // overflow on the very last query: its candidates are dropped
+      if (n_candidates) *n_candidates = 0;
+      if (last) *last = 1;
+      return first_query;
+    }
+    count = counts[first_query];
+    i = first_query + 1;
+  }
+  for (;; ++i) {
+    if (i >= n) { end = n; is_last = 1; break; }
+    count += counts[i];
+    if (count > max_list_length) { end = i; count -= counts[i]; break; }
+  }
+  if (n_candidates) *n_candidates = count;
+  if (last) *last = is_last || count == 0;  // an empty list ends the driver loop (aligner.cpp:136)
+  return end;
+}
+
+namespace {
+
+int scan_counts(gm_context *c, uint32_t first, uint32_t end, int mode, uint32_t *total) {
+  scan_kernel<<<1, 1024, 0, c->stream>>>(c->cand_cnt.p, first, end - first, c->prefix.p, mode);
+  GM_CUDA(cudaGetLastError());
+  if (total)
+    GM_CUDA(cudaMemcpyAsync(total, c->prefix.p + (end - first), 4, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+int check_range(gm_context *c, uint32_t first, uint32_t end) {
+  if (int r = ensure_query_state(c)) return r;
+  if (c->cur_chunk < 0) return fail(GM_ERR_ARGUMENT, "no searched db chunk (gm_search)");
+  if (first > end || end > c->n_queries) return fail(GM_ERR_ARGUMENT, "bad query range [%u,%u)", first, end);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int gm_candidates_download(gm_context *c, uint32_t first, uint32_t end,
+                                      uint32_t *query_ids, uint32_t *starts) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = check_range(c, first, end)) return r;
+  if (first == end) return 0;
+  uint32_t total = 0;
+  if (int r = scan_counts(c, first, end, 0, &total)) return r;
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  if (total == 0) return 0;
+  GM_CUDA(c->gather0.ensure(total));
+  GM_CUDA(c->gather2.ensure(total));
+  gather_kernel<<<c->sm_count * 4, 128, 0, c->stream>>>(c->cand_off.p, c->cand_cnt.p, c->prefix.p,
+                                                        first, end - first, c->cand_start.p, nullptr,
+                                                        c->gather0.p, nullptr, c->gather2.p);
+  GM_CUDA(cudaGetLastError());
+  if (starts) GM_CUDA(cudaMemcpyAsync(starts, c->gather0.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (query_ids) GM_CUDA(cudaMemcpyAsync(query_ids, c->gather2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *scores,
+                        uint32_t *ends, gm_stats *stats) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = check_range(c, first, end)) return r;
+  if (first == end) return 0;
+  DbChunk &ch = c->chunks[c->cur_chunk];
+  GM_CUDA(c->cand_score.ensure(c->cand_capacity));
+  GM_CUDA(c->cand_end.ensure(c->cand_capacity));
+  uint32_t n_strips = 1;
+  const int rows = sw_rows_per_strip(c->query_len, &n_strips);
+  SwParams p = {};
+  p.db = ch.seq.p;
+  p.db_len = ch.seq_len;
+  p.queries = c->queries.p;
+  p.query_len = c->query_len;
+  p.first_query = first;
+  p.n_q = end - first;
+  p.task_prefix = c->prefix.p;
+  p.cand_off = c->cand_off.p;
+  p.cand_cnt = c->cand_cnt.p;
+  p.cand_start = c->cand_start.p;
+  p.cand_score = c->cand_score.p;
+  p.cand_end = c->cand_end.p;
+  p.matrix = c->matrix.p;
+  p.open_gap = c->opt.open_gap;
+  p.extend_gap = c->opt.extend_gap;
+  p.extend = c->opt.extend;
+  p.base_len = c->query_len + 2 * c->opt.extend + 2 * (1u << c->opt.log_region);  // aligner.cpp:549
+  p.n_strips = n_strips;
+  p.task_counter = c->small.p + 1;
+  p.cells = c->counters.p + 2;
+  GM_CUDA(cudaMemsetAsync(c->small.p + 1, 0, 4, c->stream));
+  GM_CUDA(cudaMemsetAsync(c->counters.p + 2, 0, 8, c->stream));
+  GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  uint32_t launches = 0;
+  if (!c->use_s32) {
+    if (n_strips > 1) {
+      const size_t need = (size_t)c->sm_count * kSwWarps * p.base_len * 96;
+      GM_CUDA(c->strip_scratch.ensure(need));
+    }
+    p.strip_scratch = c->strip_scratch.p;
+    if (int r = scan_counts(c, first, end, 1, nullptr)) return r;
+    GM_CUDA(sw_extend_launch(p, rows, c->sm_count, c->stream));
+    launches = 2;
+  } else {
+    GM_CUDA(sw_extend_s32_launch(p, c->sm_count, c->stream));
+    launches = 1;
+  }
+  GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  if (scores || ends) {
+    uint32_t total = 0;
+    if (int r = scan_counts(c, first, end, 0, &total)) return r;
+    GM_CUDA(cudaStreamSynchronize(c->stream));
+    if (total) {
+      GM_CUDA(c->gather0.ensure(total));
+      GM_CUDA(c->gather1.ensure(total));
+      gather_kernel<<<c->sm_count * 4, 128, 0, c->stream>>>(
+          c->cand_off.p, c->cand_cnt.p, c->prefix.p, first, end - first, c->cand_score.p,
+          c->cand_end.p, c->gather0.p, c->gather1.p, nullptr);
+      GM_CUDA(cudaGetLastError());
+      if (scores) GM_CUDA(cudaMemcpyAsync(scores, c->gather0.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+      if (ends) GM_CUDA(cudaMemcpyAsync(ends, c->gather1.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+      launches += 2;
+    }
+  }
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  if (stats) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    stats->ms_score += ms;
+    stats->kernel_launches += launches;
+    unsigned long long cells = 0;
+    GM_CUDA(cudaMemcpy(&cells, c->counters.p + 2, 8, cudaMemcpyDeviceToHost));
+    stats->cells += cells;
+    uint64_t n = 0;
+    for (uint32_t q = first; q < end; ++q) n += c->h_counts[q];
+    stats->candidates += n;
+  }
+  return 0;
+}
+
+extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *stats) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = check_range(c, first, end)) return r;
+  DbChunk &ch = c->chunks[c->cur_chunk];
+  const int src = c->cur_hits, dst = src ^ 1;
+  uint64_t n_new = 0;
+  for (uint32_t q = first; q < end; ++q) n_new += c->h_counts[q];
+  const uint64_t big_cap = n_new + (uint64_t)c->n_queries * c->cap + 1;
+  GM_CUDA(c->big_scratch.ensure(big_cap));
+  MergeParams p = {};
+  p.queries = c->queries.p;
+  p.query_len = c->query_len;
+  p.n_queries = c->n_queries;
+  p.run_first = c->run_first.p;
+  p.run_last = c->run_last.p;
+  p.n_runs = c->n_runs;
+  p.first_query = first;
+  p.end_query = end;
+  p.cand_off = c->cand_off.p;
+  p.cand_cnt = c->cand_cnt.p;
+  p.cand_start = c->cand_start.p;
+  p.cand_score = c->cand_score.p;
+  p.cand_end = c->cand_end.p;
+  p.db = ch.seq.p;
+  p.db_len = ch.seq_len;
+  p.seq_starts = ch.seq_starts.p;
+  p.n_seqs = ch.n_seqs;
+  p.db_chunk = (uint32_t)c->cur_chunk;
+  p.old_hits = c->hits[src].p;
+  p.old_cnt = c->hit_cnt[src].p;
+  p.new_hits = c->hits[dst].p;
+  p.new_cnt = c->hit_cnt[dst].p;
+  p.cap = c->cap;
+  p.best = c->opt.best;
+  p.jobs = c->jobs.p;
+  p.n_jobs = c->small.p + 3;
+  p.big_scratch = c->big_scratch.p;
+  p.big_capacity = big_cap;
+  p.big_cursor = c->counters.p + 3;
+  p.error = reinterpret_cast<int *>(c->small.p + 4);
+  p.run_counter = c->small.p + 5;
+  p.smem_elems = 1536;
+  GM_CUDA(cudaMemsetAsync(c->small.p + 3, 0, 3 * 4, c->stream));
+  GM_CUDA(cudaMemsetAsync(c->counters.p + 3, 0, 8, c->stream));
+  GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  GM_CUDA(merge_launch(p, c->sm_count, c->stream));
+  GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+
+  TracebackParams t = {};
+  t.queries = c->queries.p;
+  t.query_len = c->query_len;
+  t.db = ch.seq.p;
+  t.seq_starts = ch.seq_starts.p;
+  t.hits = c->hits[dst].p;
+  t.jobs = c->jobs.p;
+  t.n_jobs = c->small.p + 3;
+  t.matrix = c->matrix.p;
+  t.open_gap = c->opt.open_gap;
+  t.extend_gap = c->opt.extend_gap;
+  t.base_len = c->query_len + 2 * c->opt.extend * 2 * (1u << c->opt.log_region);  // aligner.cpp:775
+  const size_t tb_threads = (size_t)traceback_grid(c->sm_count) * traceback_threads();
+  GM_CUDA(c->tb_work.ensure(tb_threads * 4 * (c->query_len + 1)));
+  t.work = c->tb_work.p;
+  GM_CUDA(traceback_launch(t, c->sm_count, c->stream));
+  GM_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  uint32_t small[8];
+  GM_CUDA(cudaMemcpyAsync(small, c->small.p, sizeof(small), cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  if (small[4]) return fail(GM_ERR_CAPACITY, "merge scratch exhausted");
+  c->cur_hits = dst;
+  if (stats) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    stats->ms_merge += ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+    stats->ms_traceback += ms;
+    stats->tracebacks += small[3];
+    stats->kernel_launches += 2;
+    stats->candidate_chunks += 1;
+  }
+  return 0;
+}
+
+extern "C" int gm_align_chunk(gm_context *c, uint32_t id, gm_stats *stats) {
+  uint64_t total = 0;
+  if (int r = gm_search(c, id, nullptr, &total, stats)) return r;
+  uint32_t first = 0;
+  while (true) {
+    uint64_t n = 0;
+    int last = 0;
+    const uint32_t end = gm_chunk_rule(c->h_counts.data(), c->n_queries, first,
+                                       c->opt.max_list_length, &n, &last);
+    if (n == 0) break;  // aligner.cpp:136-139
+    if (int r = gm_score(c, first, end, nullptr, nullptr, stats)) return r;
+    if (int r = gm_merge(c, first, end, stats)) return r;
+    if (last) break;
+    first = end;
+  }
+  return 0;
+}
+
+extern "C" int gm_results_download(gm_context *c, gm_hit *hits, uint32_t *counts) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  if (hits)
+    GM_CUDA(cudaMemcpyAsync(hits, c->hits[c->cur_hits].p, (size_t)c->n_queries * c->cap * sizeof(gm_hit),
+                            cudaMemcpyDeviceToHost, c->stream));
+  if (counts)
+    GM_CUDA(cudaMemcpyAsync(counts, c->hit_cnt[c->cur_hits].p, (size_t)c->n_queries * 4,
+                            cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gm_results_upload(gm_context *c, const gm_hit *hits, const uint32_t *counts) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  if (!hits || !counts) return fail(GM_ERR_ARGUMENT, "null hit lists");
+  GM_CUDA(cudaMemcpyAsync(c->hits[c->cur_hits].p, hits, (size_t)c->n_queries * c->cap * sizeof(gm_hit),
+                          cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(cudaMemcpyAsync(c->hit_cnt[c->cur_hits].p, counts, (size_t)c->n_queries * 4,
+                          cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gm_db_build_index(gm_context *c, uint32_t id, const uint8_t *seq, uint32_t seq_len,
+                                 const uint32_t *seq_starts, uint32_t n_seqs, uint32_t seed) {
+  if (int r = check_ctx(c)) return r;
+  if (id >= GM_MAX_DB_CHUNKS) return fail(GM_ERR_ARGUMENT, "chunk id %u out of range", id);
+  if (!seq || !seq_starts || n_seqs == 0 || seed == 0) return fail(GM_ERR_ARGUMENT, "bad index input");
+  DbChunk &ch = c->chunks[id];
+  ch.valid = false;
+  uint32_t weight = 0;
+  for (uint32_t s = seed; s; s >>= 1) weight += s & 1;
+  if (weight > 6) return fail(GM_ERR_UNSUPPORTED, "seed weight %u too large", weight);
+  const uint32_t n_keys = 1u << (kCharBits * weight);
+  GM_CUDA(ch.seq.ensure(seq_len));
+  GM_CUDA(ch.seq_starts.ensure(n_seqs));
+  GM_CUDA(ch.keys_count.ensure((size_t)n_keys + 1));
+  GM_CUDA(ch.positions.ensure(seq_len));
+  GM_CUDA(cudaMemcpyAsync(ch.seq.p, seq, seq_len, cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(cudaMemcpyAsync(ch.seq_starts.p, seq_starts, (size_t)n_seqs * 4, cudaMemcpyHostToDevice, c->stream));
+  DevBuf<uint32_t> keys, keys_sorted, pos;
+  DevBuf<unsigned char> temp;
+  GM_CUDA(keys.ensure(seq_len));
+  GM_CUDA(keys_sorted.ensure(seq_len));
+  GM_CUDA(pos.ensure(seq_len));
+  index_keys_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(ch.seq.p, seq_len, ch.seq_starts.p, n_seqs,
+                                                            seed, seed_length_of(seed), keys.p, pos.p);
+  GM_CUDA(cudaGetLastError());
+  size_t temp_bytes = 0;
+  GM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys.p, keys_sorted.p, pos.p,
+                                          ch.positions.p, (int)seq_len, 0, 32, c->stream));
+  GM_CUDA(temp.ensure(temp_bytes));
+  GM_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, keys.p, keys_sorted.p, pos.p,
+                                          ch.positions.p, (int)seq_len, 0, 32, c->stream));
+  index_bounds_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(keys_sorted.p, seq_len, n_keys,
+                                                              ch.keys_count.p);
+  GM_CUDA(cudaGetLastError());
+  uint32_t n_pos = 0;
+  GM_CUDA(cudaMemcpyAsync(&n_pos, ch.keys_count.p + n_keys, 4, cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  keys.release(); keys_sorted.release(); pos.release(); temp.release();
+  ch.seq_len = seq_len;
+  ch.n_seqs = n_seqs;
+  ch.keys_count_len = n_keys + 1;
+  ch.positions_len = n_pos;
+  ch.valid = true;
+  if (c->cur_chunk == (int)id) c->cur_chunk = -1;
+  return 0;
+}
+
+extern "C" int gm_db_download_index(gm_context *c, uint32_t id, uint32_t *keys_count,
+                                    uint32_t *positions, uint32_t *positions_len) {
+  if (int r = check_ctx(c)) return r;
+  if (id >= GM_MAX_DB_CHUNKS || !c->chunks[id].valid)
+    return fail(GM_ERR_ARGUMENT, "db chunk %u is not resident", id);
+  DbChunk &ch = c->chunks[id];
+  if (keys_count)
+    GM_CUDA(cudaMemcpyAsync(keys_count, ch.keys_count.p, (size_t)ch.keys_count_len * 4,
+                            cudaMemcpyDeviceToHost, c->stream));
+  if (positions)
+    GM_CUDA(cudaMemcpyAsync(positions, ch.positions.p, (size_t)ch.positions_len * 4,
+                            cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  if (positions_len) *positions_len = ch.positions_len;
+  return 0;
+}
+
+// =========================================================================================
+// legacy drop-in: reference aligner_gpu.h:32-117 on one process-wide context
+// =========================================================================================
+
+namespace {
+
+gm_context *g_legacy = nullptr;
+gm_options g_legacy_opt;
+bool g_legacy_have_matrix = false;
+int g_legacy_device = 0;
+std::vector<uint32_t> g_legacy_counts;   // per-query counts of the current db chunk
+bool g_legacy_searched = false;
+uint32_t g_legacy_first = 0, g_legacy_end = 0;
+uint32_t g_legacy_n_seqs_dummy[1] = {0};
+
+void legacy_die(const char *what) {  // aligner_gpu.h:135-141
+  fprintf(stderr, "Cuda error in ghostm_b200 (%s) : %s.\n", what, gm_last_error());
+  exit(EXIT_FAILURE);
+}
+
+void legacy_ensure() {
+  if (!g_legacy && gm_create(g_legacy_device, &g_legacy) != 0) legacy_die("gm_create");
+}
+
+}  // namespace
+
+extern "C" int InitGpu(void) { return 0; }
+
+extern "C" size_t GetNeededGPUMemorySize(uint32_t seed, uint32_t shift_size, uint32_t max_list_length,
+                                         uint32_t max_query_length, uint32_t max_number_queries,
+                                         uint32_t max_db_length) {
+  (void)shift_size;
+  uint32_t weight = 0;
+  for (uint32_t s = seed; s; s >>= 1) weight += s & 1;
+  size_t bytes = 0;
+  bytes += (size_t)max_db_length * 5;                              // residues + positions
+  bytes += ((size_t)1 << (kCharBits * weight)) * 4 + 4;            // keys_count
+  bytes += (size_t)max_query_length * max_number_queries;          // queries
+  bytes += (size_t)max_number_queries * 4 * 3;                     // per-query counts/offsets/prefix
+  bytes += (size_t)std::max<uint32_t>(max_list_length, 1u << 20) * 4 * 3;  // starts, scores, ends
+  bytes += (size_t)64 << 20;                                       // staging + slack
+  return bytes;
+}
+
+extern "C" int CheckGpuMemory(uint32_t seed, uint32_t shift_size, uint32_t max_list_length,
+                              uint32_t max_query_length, uint32_t max_number_queries,
+                              uint32_t max_db_length) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 1;
+  return GetNeededGPUMemorySize(seed, shift_size, max_list_length, max_query_length,
+                                max_number_queries, max_db_length) > free_b;
+}
+
+extern "C" int SetOptionGpu(uint32_t max_list_length, int score_matrix[], int device) {
+  g_legacy_device = device;
+  if (g_legacy && g_legacy->device != device) { gm_destroy(g_legacy); g_legacy = nullptr; }
+  legacy_ensure();
+  memset(&g_legacy_opt, 0, sizeof(g_legacy_opt));
+  g_legacy_opt.max_list_length = max_list_length;
+  memcpy(g_legacy_opt.score_matrix, score_matrix, sizeof(g_legacy_opt.score_matrix));
+  g_legacy_have_matrix = true;
+  // the candidate store must hold every candidate of one (query chunk, db chunk) pair
+  const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_list_length * 2, 1u << 20),
+                                          (1ull << 32) - 1);
+  if (gm_set_candidate_capacity(g_legacy, cap) != 0) legacy_die("gm_set_candidate_capacity");
+  return 0;
+}
+
+extern "C" void printGpuInfo(int device) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return;
+  printf("  GPU [%d] %s, %d SMs, %.1f GiB, sm_%d%d (ghostm_b200)\n", device, prop.name,
+         prop.multiProcessorCount, prop.totalGlobalMem / 1073741824.0, prop.major, prop.minor);
+}
+
+namespace {
+// queries are kept on the host until the search options arrive with SearchNextGpu
+std::vector<uint8_t> g_legacy_queries;
+uint32_t g_legacy_nq = 0, g_legacy_ql = 0;
+bool g_legacy_queries_dirty = false;
+}  // namespace
+
+extern "C" int SetQueryGpu(uint8_t sequences[], uint32_t number_sequences, uint32_t sequence_length) {
+  legacy_ensure();
+  g_legacy_queries.assign(sequences, sequences + (size_t)number_sequences * sequence_length);
+  g_legacy_nq = number_sequences;
+  g_legacy_ql = sequence_length;
+  g_legacy_queries_dirty = true;
+  return 0;
+}
+
+extern "C" int SetDbGpu(uint8_t sequences[], uint32_t sequences_length, uint32_t keys_count[],
+                        uint32_t keys_count_length, uint32_t positions[], uint32_t positions_length) {
+  legacy_ensure();
+  // the legacy boundary does not pass the .pos table; Merge stays on the caller's side
+  if (gm_db_upload(g_legacy, 0, sequences, sequences_length, keys_count, keys_count_length, positions,
+                   positions_length, g_legacy_n_seqs_dummy, 1) != 0)
+    legacy_die("SetDbGpu");
+  g_legacy_searched = false;
+  return 0;
+}
+
+extern "C" uint32_t SearchNextGpu(uint32_t query_sequence_length, uint32_t number_query_sequences,
+                                  uint32_t seed, uint32_t threshold, uint32_t shift_size,
+                                  uint32_t log_region_size, uint32_t max_number_alignments,
+                                  uint32_t start_query_id, uint32_t *alignment_count_list,
+                                  uint32_t *starts) {
+  legacy_ensure();
+  if (start_query_id >= number_query_sequences) return 0;               // aligner_gpu.cu:787
+  if (start_query_id == 0 || !g_legacy_searched) {                      // aligner_gpu.cu:814
+    g_legacy_opt.seed = seed;
+    g_legacy_opt.threshold = threshold;
+    g_legacy_opt.shift = shift_size;
+    g_legacy_opt.log_region = log_region_size;
+    g_legacy_opt.max_list_length = max_number_alignments;
+    g_legacy_opt.best = 1;
+    g_legacy_opt.open_gap = -11;   // refined by CalculateScoreGpu, which receives the real values
+    g_legacy_opt.extend_gap = -1;
+    if (gm_set_options(g_legacy, &g_legacy_opt) != 0) legacy_die("SearchNextGpu/options");
+    if (g_legacy_queries_dirty || g_legacy->n_queries != number_query_sequences ||
+        g_legacy->query_len != query_sequence_length) {
+      if (g_legacy_nq != number_query_sequences || g_legacy_ql != query_sequence_length) {
+        g_error = "SearchNextGpu: query shape differs from SetQueryGpu";
+        legacy_die("SearchNextGpu");
+      }
+      if (gm_query_upload(g_legacy, g_legacy_queries.data(), g_legacy_nq, g_legacy_ql, nullptr) != 0)
+        legacy_die("SearchNextGpu/queries");
+      g_legacy_queries_dirty = false;
+    }
+    g_legacy_counts.assign(number_query_sequences, 0);
+    if (gm_search(g_legacy, 0, g_legacy_counts.data(), nullptr, nullptr) != 0)
+      legacy_die("SearchNextGpu/search");
+    g_legacy_searched = true;
+  }
+  // The reference caller advances start_query_id by the returned count (aligner.cpp:376), so
+  // the overflowing query is simply the first query of the next call; its candidates are
+  // counted against the next budget exactly like the CPU path's carried list.
+  uint64_t n = 0;
+  int last = 0;
+  const uint32_t end = gm_chunk_rule(g_legacy_counts.data(), number_query_sequences, start_query_id,
+                                     max_number_alignments, &n, &last);
+  if (n == 0) return 0;
+  g_legacy_first = start_query_id;
+  g_legacy_end = end;
+  uint32_t cum = 0;
+  alignment_count_list[0] = 0;
+  for (uint32_t q = start_query_id; q < end; ++q) {
+    cum += g_legacy_counts[q];
+    alignment_count_list[q - start_query_id + 1] = cum;
+  }
+  if (gm_candidates_download(g_legacy, start_query_id, end, nullptr, starts) != 0)
+    legacy_die("SearchNextGpu/download");
+  return end - start_query_id;
+}
+
+extern "C" void CalculateScoreGpu(uint32_t db_length, uint32_t query_sequence_length,
+                                  uint32_t number_alignment_list, uint32_t scores[], uint32_t ends[],
+                                  uint32_t base_search_length, uint32_t offset, int open_gap,
+                                  int extend_gap) {
+  (void)db_length;
+  (void)query_sequence_length;
+  legacy_ensure();
+  if (number_alignment_list == 0) return;
+  // base_search_length = L + 2*extend + 2*2^r (aligner.cpp:527) is re-derived from the options
+  (void)base_search_length;
+  g_legacy_opt.extend = offset;
+  g_legacy_opt.open_gap = open_gap;
+  g_legacy_opt.extend_gap = extend_gap;
+  if (gm_set_options(g_legacy, &g_legacy_opt) != 0) legacy_die("CalculateScoreGpu/options");
+  if (gm_score(g_legacy, g_legacy_first, g_legacy_end, scores, ends, nullptr) != 0)
+    legacy_die("CalculateScoreGpu");
+}
+
+extern "C" int FreeGpu(void) {
+  if (g_legacy) gm_destroy(g_legacy);
+  g_legacy = nullptr;
+  g_legacy_searched = false;
+  return 0;
+}

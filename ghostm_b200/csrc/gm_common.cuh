@@ -1,0 +1,116 @@
+// Shared declarations of the ghostm_b200 device code (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ghostm_b200.h"
+
+namespace gm {
+
+constexpr int kAlphabet = 32;     // reference common.h:31
+constexpr int kCharBits = 5;      // common.h:32
+constexpr uint8_t kSeqEnd = 25;   // common.h:34
+constexpr uint8_t kBaseX = 23;    // common.h:35
+constexpr uint32_t kNoId = 0xFFFFFFFFu;
+
+// ---- SW extension ---------------------------------------------------------------------
+constexpr int kSwThreads = 256;          // 8 warps per CTA, one CTA per SM (register bound)
+constexpr int kSwWarps = kSwThreads / 32;
+constexpr int kSwCandPerTask = 64;       // one warp task = 64 candidates of ONE query (2 per lane)
+constexpr int kSwMaxRows = 80;           // rows (query residues) held in registers per strip
+
+struct SwParams {
+  const uint8_t *db;
+  uint32_t db_len;
+  const uint8_t *queries;      // [n_queries][query_len]
+  uint32_t query_len;
+  uint32_t first_query;        // tasks cover queries [first_query, first_query + n_q)
+  uint32_t n_q;
+  const uint32_t *task_prefix; // [n_q + 1] exclusive prefix of ceil(cnt/64)
+  const uint32_t *cand_off;    // [n_queries] first candidate of each query in cand_* arrays
+  const uint32_t *cand_cnt;    // [n_queries]
+  const uint32_t *cand_start;  // candidate db offsets (region starts)
+  uint32_t *cand_score;        // out
+  uint32_t *cand_end;          // out
+  const int32_t *matrix;       // [32*32], row = db residue, column = query residue
+  int open_gap, extend_gap;    // negative
+  uint32_t extend;             // -e
+  uint32_t base_len;           // L + 2*extend + 2*2^r  (aligner.cpp:549)
+  uint32_t n_strips;           // ceil(query_len / R)
+  uint32_t *task_counter;      // dynamic task fetch
+  uint32_t *strip_scratch;     // boundary rows between strips (n_strips > 1)
+  unsigned long long *cells;   // += L * clipped window per candidate
+};
+
+// ---- seed search ----------------------------------------------------------------------
+struct SearchParams {
+  const uint8_t *queries;
+  uint32_t query_len, n_queries;
+  const uint32_t *keys_count;
+  const uint32_t *positions;
+  uint32_t seed, seed_len, shift, log_region, threshold, list_len;
+  uint32_t n_regions;          // regions of the chunk: (seq_len >> log_region) + 1
+  uint32_t tile_regions;       // regions per shared-memory tile (multiple of 1024)
+  uint32_t *cand_off, *cand_cnt;
+  uint32_t *cand_start;
+  unsigned long long cand_capacity;
+  unsigned long long *cand_cursor;   // global append cursor
+  uint32_t *staging;           // [gridDim.x][staging_cap]
+  uint32_t staging_cap;
+  uint32_t *query_counter;     // dynamic query fetch
+  unsigned long long *positions_visited;
+  int *overflow;               // set when cand_capacity is exceeded
+};
+
+// ---- merge / traceback --------------------------------------------------------------
+struct MergeParams {
+  // queries / runs
+  const uint8_t *queries;
+  uint32_t query_len, n_queries;
+  const uint32_t *run_first;   // [n_runs] first query of each same-name run
+  const uint32_t *run_last;    // [n_runs] last query of the run (where the list lives)
+  uint32_t n_runs;
+  uint32_t first_query, end_query;   // queries with new candidates in this call
+  // scored candidates
+  const uint32_t *cand_off, *cand_cnt, *cand_start, *cand_score, *cand_end;
+  // db chunk
+  const uint8_t *db;
+  uint32_t db_len;
+  const uint32_t *seq_starts;
+  uint32_t n_seqs, db_chunk;
+  // hit lists (old -> new), cap records per query
+  const gm_hit *old_hits;
+  const uint32_t *old_cnt;
+  gm_hit *new_hits;
+  uint32_t *new_cnt;
+  uint32_t cap, best;
+  // traceback job queue
+  uint32_t *jobs;              // slot index = query * cap + k
+  uint32_t *n_jobs;
+  // overflow area for runs that do not fit the shared-memory list
+  unsigned long long *big_scratch;
+  unsigned long long big_capacity;
+  unsigned long long *big_cursor;
+  int *error;                  // set on scratch exhaustion
+  uint32_t *run_counter;
+  uint32_t smem_elems;         // list capacity per warp in shared memory (u32 records)
+};
+
+struct TracebackParams {
+  const uint8_t *queries;
+  uint32_t query_len;
+  const uint8_t *db;
+  const uint32_t *seq_starts;
+  gm_hit *hits;
+  const uint32_t *jobs;
+  const uint32_t *n_jobs;
+  const int32_t *matrix;
+  int open_gap, extend_gap;
+  uint32_t base_len;           // L + 2*extend*2*2^r  (aligner.cpp:775)
+  int *work;                   // [threads][4][L+1] column state
+};
+
+
+}  // namespace gm

@@ -1,0 +1,412 @@
+// Merge (exact top-`best` selection) and TraceBack on the device, sm_100a.
+//
+// Merge semantics: reference Aligner::Merge, aligner.cpp:687-769.  For every run of equally
+// named queries the list l = [new candidates of the run's queries in (query, region) order] ++
+// [hits carried from earlier calls] is sorted with std::sort and the comparator "score
+// descending" (aligner.cpp:52-63), then walked: carried hits pass, new hits pass once per db
+// sequence (DB::GetID of the forward end, db.h:94-120), the walk stops at `best` hits; the list
+// lives at the last query of the run.  std::sort is unstable, so which of several equal-score
+// candidates survives depends on the exact algorithm: libstdc++'s introsort (bits/stl_algo.h,
+// threshold 16, median-of-3 to first, unguarded Hoare partition, heapsort at depth 2*lg n,
+// final insertion sort) is REPLAYED here move for move on (score, list index) records.  One warp
+// owns one run; lane 0 executes the replay in shared memory, the warp builds the list and
+// copies records cooperatively.  Selection never depends on TraceBack's output, so accepted new
+// hits are queued and traced by a second kernel.
+//
+// TraceBack semantics: reference Aligner::TraceBack, aligner.cpp:771-949: reverse affine SW from
+// the forward end over at most L + 2*extend*2*2^r columns, stop at the first SEQUENCE_END,
+// track match count and alignment length along the argmax path (diagonal first, then strictly
+// greater insertion, then strictly greater deletion), keep the FIRST strict maximum.
+#include "gm_common.cuh"
+
+namespace gm {
+
+namespace {
+
+constexpr int kMergeThreads = 512;
+constexpr int kMergeWarps = kMergeThreads / 32;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr uint32_t kCarriedFlag = 0x8000u;  // payload bit: record refers to a carried hit
+
+// ---- libstdc++ 13 std::sort, replayed.  Rec is u32 (score<<16 | ref) or u64 (score<<32 | ref);
+// only the score takes part in comparisons, exactly like AlignmentComp.
+template <typename Rec> struct RecKey;
+template <> struct RecKey<uint32_t> {
+  static __device__ __forceinline__ uint32_t key(uint32_t r) { return r >> 16; }
+};
+template <> struct RecKey<unsigned long long> {
+  static __device__ __forceinline__ uint32_t key(unsigned long long r) { return (uint32_t)(r >> 32); }
+};
+
+template <typename Rec>
+__device__ __forceinline__ bool comp(Rec a, Rec b) {  // aligner.cpp:52-63: a.score > b.score
+  return RecKey<Rec>::key(a) > RecKey<Rec>::key(b);
+}
+
+template <typename Rec>
+__device__ void push_heap_(Rec *first, long hole, long top, Rec value) {
+  long parent = (hole - 1) / 2;
+  while (hole > top && comp(first[parent], value)) {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+
+template <typename Rec>
+__device__ void adjust_heap_(Rec *first, long hole, long len, Rec value) {
+  const long top = hole;
+  long second = hole;
+  while (second < (len - 1) / 2) {
+    second = 2 * (second + 1);
+    if (comp(first[second], first[second - 1])) second--;
+    first[hole] = first[second];
+    hole = second;
+  }
+  if ((len & 1) == 0 && second == (len - 2) / 2) {
+    second = 2 * (second + 1);
+    first[hole] = first[second - 1];
+    hole = second - 1;
+  }
+  push_heap_(first, hole, top, value);
+}
+
+template <typename Rec>
+__device__ void heap_sort_(Rec *first, Rec *last) {  // __partial_sort(first, last, last)
+  const long len = last - first;
+  if (len >= 2) {
+    long parent = (len - 2) / 2;
+    while (true) {
+      const Rec value = first[parent];
+      adjust_heap_(first, parent, len, value);
+      if (parent == 0) break;
+      parent--;
+    }
+  }
+  while (last - first > 1) {
+    --last;
+    const Rec value = *last;
+    *last = *first;
+    adjust_heap_(first, 0L, (long)(last - first), value);
+  }
+}
+
+template <typename Rec>
+__device__ __forceinline__ void swap_(Rec *a, Rec *b) {
+  const Rec t = *a;
+  *a = *b;
+  *b = t;
+}
+
+template <typename Rec>
+__device__ void unguarded_linear_insert_(Rec *last) {
+  const Rec val = *last;
+  Rec *next = last - 1;
+  while (comp(val, *next)) {
+    *last = *next;
+    last = next;
+    --next;
+  }
+  *last = val;
+}
+
+template <typename Rec>
+__device__ void insertion_sort_(Rec *first, Rec *last) {
+  if (first == last) return;
+  for (Rec *i = first + 1; i != last; ++i) {
+    if (comp(*i, *first)) {
+      const Rec val = *i;
+      for (Rec *p = i; p != first; --p) *p = *(p - 1);  // move_backward(first, i, i + 1)
+      *first = val;
+    } else {
+      unguarded_linear_insert_(i);
+    }
+  }
+}
+
+template <typename Rec>
+__device__ void std_sort_replay(Rec *first, long n) {
+  if (n <= 0) return;
+  Rec *last = first + n;
+  // __introsort_loop with an explicit stack for the (cut, last) halves
+  struct Frame { Rec *first, *last; int depth; };
+  Frame stack[64];
+  int sp = 0;
+  int lg = 0;
+  for (long m = n; m > 1; m >>= 1) ++lg;
+  stack[sp++] = Frame{first, last, lg * 2};
+  while (sp > 0) {
+    Frame fr = stack[--sp];
+    Rec *f = fr.first, *l = fr.last;
+    int depth = fr.depth;
+    // The reference recursion handles [cut, last) first, then loops on [first, cut).  The two
+    // halves are disjoint and each is processed independently of the other, so any order of
+    // handling gives the same final array; an explicit stack keeps it iterative.
+    while (l - f > 16) {
+      if (depth == 0) {
+        heap_sort_(f, l);
+        break;
+      }
+      --depth;
+      Rec *mid = f + (l - f) / 2;
+      Rec *a = f + 1, *b = mid, *c = l - 1;  // __move_median_to_first(f, a, b, c)
+      if (comp(*a, *b)) {
+        if (comp(*b, *c)) swap_(f, b);
+        else if (comp(*a, *c)) swap_(f, c);
+        else swap_(f, a);
+      } else if (comp(*a, *c)) swap_(f, a);
+      else if (comp(*b, *c)) swap_(f, c);
+      else swap_(f, b);
+      Rec *lo = f + 1, *hi = l;                // __unguarded_partition(f + 1, l, f)
+      const Rec pivot = *f;
+      while (true) {
+        while (comp(*lo, pivot)) ++lo;
+        --hi;
+        while (comp(pivot, *hi)) --hi;
+        if (!(lo < hi)) break;
+        swap_(lo, hi);
+        ++lo;
+      }
+      Rec *cut = lo;
+      stack[sp++] = Frame{cut, l, depth};
+      l = cut;
+    }
+  }
+  if (n > 16) {  // __final_insertion_sort
+    insertion_sort_(first, first + 16);
+    for (Rec *i = first + 16; i != last; ++i) unguarded_linear_insert_(i);
+  } else {
+    insertion_sort_(first, last);
+  }
+}
+
+// DB::GetID, db.h:94-120
+__device__ uint32_t db_get_id(const uint32_t *pos, uint32_t n_seqs, uint32_t seq_len, uint32_t position) {
+  if (pos[n_seqs - 1] <= position && position < seq_len) return n_seqs - 1;
+  if (n_seqs < 2) return kNoId;
+  uint32_t left = 0, right = n_seqs - 2;
+  while (left <= right) {
+    const uint32_t mid = (left + right) / 2;
+    if (pos[mid] <= position && position < pos[mid + 1]) return mid;
+    if (pos[mid] < position) {
+      left = mid + 1;
+    } else {
+      if (mid == 0) break;
+      right = mid - 1;
+    }
+  }
+  return kNoId;
+}
+
+template <typename Rec>
+__device__ void merge_run(const MergeParams &p, Rec *list, uint32_t n_new, uint32_t n_old,
+                          uint32_t qf, uint32_t ql, uint32_t lane) {
+  constexpr bool kWide = sizeof(Rec) == 8;
+  const uint32_t n = n_new + n_old;
+  // ---- build the list in reference order (aligner.cpp:732-740)
+  uint32_t fill = 0;
+  for (uint32_t q = qf; q <= ql; ++q) {
+    if (q < p.first_query || q >= p.end_query) continue;
+    const uint32_t cnt = p.cand_cnt[q], off = p.cand_off[q];
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint32_t score = p.cand_score[off + i];
+      if (kWide) list[fill + i] = (Rec)(((unsigned long long)score << 32) | (fill + i));
+      else list[fill + i] = (Rec)((score << 16) | (fill + i));
+    }
+    fill += cnt;
+  }
+  for (uint32_t i = lane; i < n_old; i += 32) {
+    const uint32_t score = p.old_hits[(size_t)ql * p.cap + i].score;
+    if (kWide) list[n_new + i] = (Rec)(((unsigned long long)score << 32) | 0x80000000u | i);
+    else list[n_new + i] = (Rec)((score << 16) | kCarriedFlag | i);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    std_sort_replay(list, (long)n);
+    // ---- walk (aligner.cpp:703-725 / :746-768)
+    uint32_t out = 0;
+    gm_hit *dst = p.new_hits + (size_t)ql * p.cap;
+    for (uint32_t it = 0; it < n; ++it) {
+      const Rec r = list[it];
+      const uint32_t ref = kWide ? (uint32_t)r : ((uint32_t)r & 0xFFFFu);
+      const bool carried = kWide ? (ref & 0x80000000u) != 0 : (ref & kCarriedFlag) != 0;
+      if (carried) {
+        const uint32_t idx = kWide ? (ref & 0x7FFFFFFFu) : (ref & 0x7FFFu);
+        if (out < p.cap) dst[out] = p.old_hits[(size_t)ql * p.cap + idx];
+        ++out;
+      } else {
+        // locate (query, i) of list position ref
+        uint32_t q = qf, rem = ref;
+        for (;; ++q) {
+          if (q < p.first_query || q >= p.end_query) continue;
+          const uint32_t cnt = p.cand_cnt[q];
+          if (rem < cnt) break;
+          rem -= cnt;
+        }
+        const uint32_t g = p.cand_off[q] + rem;
+        const uint32_t end = p.cand_end[g];
+        const uint32_t db_id = db_get_id(p.seq_starts, p.n_seqs, p.db_len, end);
+        bool seen = false;  // overlap[db_id] == id (aligner.cpp:707): accepted earlier in this call
+        for (uint32_t k = 0; k < out && k < p.cap; ++k)
+          seen |= dst[k].db_chunk == p.db_chunk && dst[k].db_id == db_id && dst[k].aln_len == kNoId;
+        if (!seen) {
+          if (out < p.cap) {
+            gm_hit h;
+            h.query_id = q;
+            h.db_id = db_id;
+            h.db_chunk = p.db_chunk;
+            h.score = p.cand_score[g];
+            h.db_start = p.cand_start[g];
+            h.db_end = end;          // absolute; TraceBack makes both sequence-relative
+            h.aln_len = kNoId;       // marks "new in this call, traceback pending"
+            h.aln_match = kNoId;
+            h.seq_id = 0.f;
+            dst[out] = h;
+            p.jobs[atomicAdd(p.n_jobs, 1u)] = ql * p.cap + out;
+          }
+          ++out;
+        }
+      }
+      if (out >= p.best) break;  // aligner.cpp:722-724
+    }
+    p.new_cnt[ql] = out < p.cap ? out : p.cap;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams p) {
+  extern __shared__ __align__(16) uint32_t lists[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t *my_list = lists + (size_t)warp * p.smem_elems;
+  while (true) {
+    uint32_t run = 0;
+    if (lane == 0) run = atomicAdd(p.run_counter, 1u);
+    run = __shfl_sync(kFull, run, 0);
+    if (run >= p.n_runs) break;
+    const uint32_t qf = p.run_first[run], ql = p.run_last[run];
+    uint32_t n_new = 0;
+    for (uint32_t q = qf + lane; q <= ql; q += 32) {
+      if (q >= p.first_query && q < p.end_query) n_new += p.cand_cnt[q];
+      if (q != ql) p.new_cnt[q] = 0;               // aligner.cpp:741
+    }
+    n_new = __reduce_add_sync(kFull, n_new);
+    const uint32_t n_old = p.old_cnt[ql];
+    const uint32_t n = n_new + n_old;
+    if (n_new == 0 && n_old <= 16) {
+      // sorted input of <= 16 records goes through insertion sort only, which is stable:
+      // the carried list is unchanged (aligner.cpp:702 on an already sorted list).
+      for (uint32_t i = lane; i < n_old; i += 32)
+        p.new_hits[(size_t)ql * p.cap + i] = p.old_hits[(size_t)ql * p.cap + i];
+      if (lane == 0) p.new_cnt[ql] = n_old;
+      continue;
+    }
+    if (n <= p.smem_elems && n < kCarriedFlag) {
+      merge_run<uint32_t>(p, my_list, n_new, n_old, qf, ql, lane);
+    } else {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(p.big_cursor, (unsigned long long)n);
+      base = __shfl_sync(kFull, base, 0);
+      if (base + n > p.big_capacity) {
+        if (lane == 0) { atomicExch(p.error, 1); p.new_cnt[ql] = 0; }
+        continue;
+      }
+      merge_run<unsigned long long>(p, p.big_scratch + base, n_new, n_old, qf, ql, lane);
+    }
+  }
+}
+
+// One thread per accepted hit; column state in global scratch ([4][L+1] ints per thread,
+// interleaved by thread so that neighbouring threads touch neighbouring words).
+__global__ void __launch_bounds__(128) traceback_kernel(const TracebackParams p) {
+  const uint32_t n_jobs = *p.n_jobs;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int L = (int)p.query_len;
+  int *dp = p.work + tid;                        // element k of array a: dp[(a*(L+1) + k) * stride]
+#define GM_COL(a, k) dp[((size_t)(a) * (L + 1) + (k)) * stride]
+  for (uint32_t job = tid; job < n_jobs; job += stride) {
+    gm_hit h = p.hits[p.jobs[job]];
+    const uint8_t *query = p.queries + (size_t)h.query_id * L;
+    const uint32_t db_offset = h.db_end;
+    uint32_t len = p.base_len;
+    if (db_offset < len) len = db_offset + 1;                         // aligner.cpp:802-805
+    for (int k = 0; k <= L; ++k) { GM_COL(0, k) = 0; GM_COL(1, k) = 0; GM_COL(2, k) = 0; GM_COL(3, k) = 0; }
+    int max_score = 0;
+    uint32_t max_start = 0, max_match = 0, max_len = 0;
+    for (uint32_t j = 0; j < len; ++j) {
+      const uint8_t c = p.db[db_offset - j];
+      if (c == kSeqEnd) break;                                        // aligner.cpp:927-929
+      const int32_t *row = p.matrix + c * kAlphabet;
+      int temp_score = 0, del = 0;
+      uint32_t temp_match = 0, temp_len = 0;
+      // the row below (k+1) of this column, carried in registers
+      int below_h = GM_COL(0, L);
+      uint32_t below_match = (uint32_t)GM_COL(2, L), below_len = (uint32_t)GM_COL(3, L);
+      for (int k = L - 1; k >= 0; --k) {
+        const int old_h = GM_COL(0, k);
+        int ins = GM_COL(1, k);
+        const uint32_t old_match = (uint32_t)GM_COL(2, k), old_len = (uint32_t)GM_COL(3, k);
+        int local = 0;
+        uint32_t nm = 0, nl = 0;
+        const int s = temp_score + row[query[k]];
+        if (s > 0) {
+          local = s;
+          nm = temp_match + (c == query[k] ? 1u : 0u);
+          nl = temp_len + 1;
+        }
+        ins = (ins + p.extend_gap < old_h + p.open_gap) ? old_h + p.open_gap : ins + p.extend_gap;
+        if (ins > local) { local = ins; nm = old_match; nl = old_len + 1; }
+        del = (del + p.extend_gap < below_h + p.open_gap) ? below_h + p.open_gap : del + p.extend_gap;
+        if (del > local) { local = del; nm = below_match; nl = below_len + 1; }
+        temp_score = old_h;
+        temp_match = old_match;
+        temp_len = old_len;
+        GM_COL(0, k) = local;
+        GM_COL(1, k) = ins;
+        GM_COL(2, k) = (int)nm;
+        GM_COL(3, k) = (int)nl;
+        below_h = local;
+        below_match = nm;
+        below_len = nl;
+        if (local > max_score) {                                      // ">": first maximum wins
+          max_score = local;
+          max_start = j;
+          max_match = nm;
+          max_len = nl;
+        }
+      }
+    }
+    const uint32_t seq_pos = p.seq_starts[h.db_id];
+    h.db_start = db_offset - max_start - seq_pos;                     // aligner.cpp:941, :715
+    h.db_end = db_offset - seq_pos;                                   // :716
+    h.seq_id = (float)max_match / (float)(int)max_len;                // :945
+    h.aln_len = max_len;
+    h.aln_match = max_match;
+    p.hits[p.jobs[job]] = h;
+  }
+#undef GM_COL
+}
+
+}  // namespace
+
+size_t merge_smem_bytes(uint32_t elems_per_warp) { return (size_t)kMergeWarps * elems_per_warp * 4; }
+
+cudaError_t merge_launch(const MergeParams &p, int sm_count, cudaStream_t stream) {
+  const size_t smem = merge_smem_bytes(p.smem_elems);
+  cudaError_t err =
+      cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  merge_kernel<<<sm_count * 2, kMergeThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+int traceback_grid(int sm_count) { return sm_count * 8; }
+int traceback_threads() { return 128; }
+
+cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_t stream) {
+  traceback_kernel<<<traceback_grid(sm_count), traceback_threads(), 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace gm

@@ -1,0 +1,291 @@
+// Seed lookup + region-count filter + ordered candidate compaction, sm_100a.
+//
+// Semantics: reference SearchNextCpu, aligner.cpp:418-509 (GPU twins aligner_gpu.cu:86-367):
+// per query, the k-mers at offsets j*shift (j < list_len) are looked up in the CSR index
+// (index.h:86-114); every position p >= j*shift of list j marks region d = (p - j*shift) >> r,
+// each list at most once per region; with cnt(d) = number of lists marking d, every occupied
+// region d (and the virtual region 0, aligner.cpp:451) whose cnt(d) + cnt(d+1) >= threshold
+// emits the candidate d << r.  Candidates come out ascending per query.
+//
+// The reference walks this as a sequential k-way merge (twice on its GPU path).  Here the
+// histogram is built directly: a CTA owns one query at a time and sweeps the region space in
+// tiles held in shared memory as `threshold` thermometer BIT-PLANES (plane i set <=> cnt > i,
+// filled with atomicOr), so a tile covers ~0.5 M regions in <200 KB and a 128 MiB db chunk is
+// ~16 tiles.  Each list is sorted, so its slice for a tile is a contiguous run found by a
+// cursor; the runs are read with coalesced warp-wide loads (one warp per list, UNROLL loads in
+// flight).  Three sparse passes per tile touch only what the positions touch:
+//   pass 1 arrive   - first position of every (list, region) run sets the lowest clear plane;
+//   pass 2 decide   - the same positions evaluate cnt(d)+cnt(d+1) >= t from the planes and set
+//                     the emit bitmap (idempotent, no election needed);
+//   pass 3 clear    - the same positions zero the words they touched and commit the cursors.
+// Ordered compaction: one thread per 1024-region group counts the emit bits it owns, a block
+// scan gives its output slot.  A query's candidates are staged per CTA, then appended to the
+// global candidate buffer in ONE allocation, so every query's candidates are contiguous and in
+// reference order; (cand_off, cand_cnt) locate them.
+#include "gm_common.cuh"
+
+namespace gm {
+
+namespace {
+
+constexpr int kSearchThreads = 1024;
+constexpr int kSearchWarps = kSearchThreads / 32;
+constexpr int kUnroll = 4;            // warp-wide loads in flight per list visit
+constexpr int kMaxListLen = 1024;     // (L - seed_len)/shift + 1 for L <= 1024
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+struct SearchShared {
+  uint32_t cur[kMaxListLen];
+  uint32_t endp[kMaxListLen];
+  uint32_t scan[kSearchWarps];
+  uint32_t min_d, max_d;
+  uint32_t query;
+  uint32_t out_n;
+  unsigned long long base;
+  unsigned long long visited;
+};
+
+__device__ __forceinline__ uint32_t get_key(const uint8_t *s, uint32_t seed) {  // index.h:86-101
+  uint32_t key = 0;
+  for (uint32_t i = 0; seed != 0; ++i, seed >>= 1)
+    if (seed & 1) key = (key << kCharBits) | s[i];
+  return key;
+}
+
+// cnt(x) >= a  <=>  plane a-1 has bit x
+template <int T>
+__device__ __forceinline__ bool emits(const uint32_t *planes, uint32_t words, uint32_t x) {
+  const uint32_t w0 = x >> 5, b0 = 1u << (x & 31), w1 = (x + 1) >> 5, b1 = 1u << ((x + 1) & 31);
+  bool r = (planes[(T - 1) * words + w0] & b0) != 0;  // cnt(x) >= T on its own
+#pragma unroll
+  for (int a = 1; a < T; ++a)
+    r |= (planes[(a - 1) * words + w0] & b0) && (planes[(T - a - 1) * words + w1] & b1);
+  return r;
+}
+
+template <int T>
+__global__ void __launch_bounds__(kSearchThreads, 1) seed_search_kernel(const SearchParams p) {
+  extern __shared__ __align__(16) uint32_t dyn[];
+  __shared__ SearchShared sh;
+  const uint32_t M = p.tile_regions;
+  const uint32_t words = M / 32 + 1;          // +1: halo word for region base+M
+  uint32_t *planes = dyn;                     // [T][words]
+  uint32_t *emitb = dyn + T * words;          // [words]
+  uint32_t *summary = emitb + words;          // [M/1024/32 + 1] one bit per 32-word group
+  const uint32_t groups = M / 1024;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t *staging = p.staging + (size_t)blockIdx.x * p.staging_cap;
+
+  for (uint32_t i = tid; i < (T + 1) * words + groups / 32 + 1; i += kSearchThreads) dyn[i] = 0;
+  if (tid == 0) sh.visited = 0;
+  __syncthreads();
+
+  while (true) {
+    if (tid == 0) sh.query = atomicAdd(p.query_counter, 1u);
+    __syncthreads();
+    const uint32_t q = sh.query;
+    if (q >= p.n_queries) break;
+    const uint8_t *query = p.queries + (size_t)q * p.query_len;
+
+    uint32_t *out = staging;
+    uint32_t out_cap = p.staging_cap;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      // ---- lookup: interval of every query k-mer, leading positions < j*shift skipped
+      if (tid == 0) { sh.min_d = 0xFFFFFFFFu; sh.max_d = 0; sh.out_n = 0; }
+      __syncthreads();
+      unsigned long long my_visited = 0;
+      for (uint32_t j = tid; j < p.list_len; j += kSearchThreads) {
+        const uint32_t key = get_key(query + j * p.shift, p.seed);
+        uint32_t b = p.keys_count[key];
+        const uint32_t e = p.keys_count[key + 1];                       // index.h:105-114
+        const uint32_t off = j * p.shift;
+        while (b < e && p.positions[b] < off) ++b;                      // aligner.cpp:430-431
+        sh.cur[j] = b;
+        sh.endp[j] = e;
+        if (b < e) {
+          atomicMin(&sh.min_d, (p.positions[b] - off) >> p.log_region);
+          atomicMax(&sh.max_d, (p.positions[e - 1] - off) >> p.log_region);
+          my_visited += e - b;
+        }
+      }
+      __syncthreads();
+      if (attempt == 0 && my_visited) atomicAdd(&sh.visited, my_visited);
+      const uint32_t min_d = sh.min_d, max_d = sh.max_d;
+
+      if (min_d != 0xFFFFFFFFu) {
+        for (uint32_t tile = min_d / M; tile <= max_d / M; ++tile) {
+          const uint32_t base = tile * M;
+          // ---------------- passes over the tile's slice of every list
+          for (int pass = 1; pass <= 3; ++pass) {
+            for (uint32_t j = warp; j < p.list_len; j += kSearchWarps) {
+              uint32_t c = sh.cur[j];
+              const uint32_t e = sh.endp[j], off = j * p.shift;
+              uint32_t carry = 0xFFFFFFFFu;  // region of the previous position of this list
+              while (c < e) {
+                uint32_t pos[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                  const uint32_t idx = c + u * 32 + lane;
+                  pos[u] = idx < e ? __ldg(p.positions + idx) : 0xFFFFFFFFu;
+                }
+                bool done = false;
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                  const bool valid = pos[u] != 0xFFFFFFFFu;
+                  const uint32_t d = valid ? (pos[u] - off) >> p.log_region : 0xFFFFFFFFu;
+                  uint32_t dprev = __shfl_up_sync(kFull, d, 1);
+                  if (lane == 0) dprev = carry;
+                  const bool in_tile = valid && d < base + M;
+                  // run start inside the tile, or the first position of region base+M (halo)
+                  const bool mark = valid && d <= base + M && d != dprev;
+                  if (!done && mark) {
+                    const uint32_t x = d - base, w = x >> 5, bit = 1u << (x & 31);
+                    if (pass == 1) {
+                      uint32_t old = atomicOr(&planes[w], bit);
+#pragma unroll
+                      for (int t = 1; t < T; ++t)
+                        if (old & bit) old = atomicOr(&planes[t * words + w], bit); else break;
+                    } else if (pass == 2) {
+                      if (in_tile && emits<T>(planes, words, x)) {
+                        atomicOr(&emitb[w], bit);
+                        atomicOr(&summary[w >> 10], 1u << ((w >> 5) & 31));
+                      }
+                    } else {
+#pragma unroll
+                      for (int t = 0; t < T; ++t) planes[t * words + w] = 0;
+                    }
+                  }
+                  const uint32_t nin = __popc(__ballot_sync(kFull, in_tile));
+                  carry = __shfl_sync(kFull, d, 31);
+                  if (!done) {
+                    c += nin;
+                    if (nin < 32) done = true;
+                  }
+                }
+                if (done) break;
+              }
+              if (pass == 3 && lane == 0) sh.cur[j] = c;
+            }
+            __syncthreads();
+            if (pass == 1 && tile == 0 && tid == 0) {
+              // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an
+              // unoccupied region 0 still emits when region 1 alone reaches the threshold.
+              if (!(planes[0] & 1u) && (planes[(T - 1) * words] & 2u)) {
+                emitb[0] |= 1u;
+                summary[0] |= 1u;
+              }
+            }
+            if (pass == 1) __syncthreads();
+          }
+          // ---------------- ordered compaction of the emit bitmap
+          uint32_t mine = 0;
+          const bool owner = tid < groups && (summary[tid >> 5] >> (tid & 31) & 1u);
+          if (owner)
+            for (uint32_t w = 0; w < 32; ++w) mine += __popc(emitb[tid * 32 + w]);
+          uint32_t incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+          }
+          if (lane == 31) sh.scan[warp] = incl;
+          __syncthreads();
+          uint32_t before = sh.out_n;
+          for (uint32_t w = 0; w < warp; ++w) before += sh.scan[w];
+          uint32_t slot = before + incl - mine;
+          if (owner) {
+            for (uint32_t w = 0; w < 32; ++w) {
+              uint32_t bits = emitb[tid * 32 + w];
+              emitb[tid * 32 + w] = 0;
+              while (bits) {
+                const uint32_t b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (slot < out_cap) out[slot] = (base + tid * 32 * 32 + w * 32 + b) << p.log_region;
+                ++slot;
+              }
+            }
+          }
+          __syncthreads();
+          if (tid == 0) {
+            uint32_t total = sh.out_n;
+            for (uint32_t w = 0; w < kSearchWarps; ++w) total += sh.scan[w];
+            sh.out_n = total;
+          }
+          if (tid < groups / 32 + 1) summary[tid] = 0;
+          if (tid == 0) planes[words - 1] = 0;   // halo word of plane 0 .. T-1
+          if (tid < T) planes[tid * words + words - 1] = 0;
+          __syncthreads();
+        }
+      }
+      // ---- hand the query's candidates over
+      const uint32_t n = sh.out_n;
+      if (attempt == 0) {
+        if (tid == 0) {
+          sh.base = n ? atomicAdd(p.cand_cursor, (unsigned long long)n) : 0ull;
+          if (n && sh.base + n > p.cand_capacity) atomicExch(p.overflow, 1);
+        }
+        __syncthreads();
+        const unsigned long long base = sh.base;
+        const bool fits = base + n <= p.cand_capacity;
+        if (tid == 0) {
+          p.cand_off[q] = (uint32_t)base;
+          p.cand_cnt[q] = fits ? n : 0u;
+        }
+        if (!fits || n == 0) break;
+        if (n <= p.staging_cap) {
+          for (uint32_t i = tid; i < n; i += kSearchThreads) p.cand_start[base + i] = staging[i];
+          break;
+        }
+        // more candidates than the staging area holds: redo the query writing in place
+        out = p.cand_start + base;
+        out_cap = n;
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && sh.visited) atomicAdd(p.positions_visited, sh.visited);
+}
+
+// Generic dynamic shared memory size for a tile of M regions.
+size_t search_smem_bytes(int T, uint32_t M) {
+  const uint32_t words = M / 32 + 1;
+  return ((size_t)(T + 1) * words + M / 1024 / 32 + 1) * sizeof(uint32_t);
+}
+
+}  // namespace
+
+// Largest tile (multiple of 1024 regions, at most 1024 groups) that fits `smem_limit`.
+uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions) {
+  uint32_t m = 1024u * 1024u;
+  while (m > 1024 && search_smem_bytes(T, m) + sizeof(SearchShared) + 256 > smem_limit) m -= 1024;
+  const uint32_t need = ((n_regions + 1023) / 1024) * 1024;
+  return m < need ? m : (need ? need : 1024);
+}
+
+cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream) {
+  const int T = (int)p.threshold;
+  const size_t smem = search_smem_bytes(T, p.tile_regions);
+  cudaError_t err = cudaSuccess;
+#define GM_LAUNCH_SEARCH(TT)                                                                   \
+  case TT:                                                                                     \
+    err = cudaFuncSetAttribute(seed_search_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               (int)smem);                                                     \
+    if (err != cudaSuccess) return err;                                                        \
+    seed_search_kernel<TT><<<grid, kSearchThreads, smem, stream>>>(p);                         \
+    break;
+  switch (T) {
+    GM_LAUNCH_SEARCH(1)
+    GM_LAUNCH_SEARCH(2)
+    GM_LAUNCH_SEARCH(3)
+    GM_LAUNCH_SEARCH(4)
+    default: return cudaErrorInvalidValue;
+  }
+#undef GM_LAUNCH_SEARCH
+  return cudaGetLastError();
+}
+
+int search_max_list_len() { return kMaxListLen; }
+int search_max_threshold() { return 4; }
+
+}  // namespace gm

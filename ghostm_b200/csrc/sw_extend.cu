@@ -1,0 +1,264 @@
+// Windowed affine-gap Smith-Waterman extension (the dominant kernel), sm_100a.
+//
+// Semantics: reference CalculateScoreCpu, aligner.cpp:545-685 (GPU twin aligner_gpu.cu:369-504):
+// for every candidate, local alignment of the L query rows against the db window
+// [start-extend, start-extend + L + 2*extend + 2*2^r) clipped to the chunk, a gap of length n
+// costing |open| + (n-1)*|extend|, both DP columns reset to 0 at SEQUENCE_END while the running
+// maximum survives, result = (max score, db offset of the LAST column that attains it).
+//
+// Design (DESIGN.md "SW extension"):
+//  * inter-candidate SIMD: every thread owns TWO candidates of the same query, one per half of
+//    a packed s16x2 word, and runs the whole DP for them with the column state (H+open, E)
+//    of up to R=80 query rows in registers.  No shuffles, no shared-memory DP state.
+//  * per cell (x2 candidates) 6 ALU-pipe DPX ops: VIADDMNMX.S16x2 (x4, one with .RELU),
+//    VIADD.16x2, VIMNMX.S16x2; the vertical (F) recurrence is restated so that its loop-carried
+//    dependency is ONE VIADDMNMX per row.
+//  * one warp task = 64 candidates of one query, so the query profile T[row][db residue]
+//    (16-bit, in shared memory, per warp) is read at bank = residue: conflict free, and the two
+//    halves are packed with one IMAD (FMA pipe), off the ALU pipe that bounds the kernel.
+//  * SEQUENCE_END columns and clipped windows are handled by a warp-uniform slow path that
+//    masks the affected half; queries longer than R rows run as horizontal strips whose
+//    boundary row (H+open, F, column max) goes through an L2-resident scratch.
+//  * scores fit s16: the host refuses option sets where L * max(matrix) could overflow.
+#include "gm_common.cuh"
+
+namespace gm {
+
+namespace {
+
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t pack2(int v) { return (uint32_t)(v & 0xFFFF) * 0x10001u; }
+
+template <int R>
+__global__ void __launch_bounds__(kSwThreads, 1) sw_extend_dpx_kernel(const SwParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int16_t *matT = reinterpret_cast<int16_t *>(smem_raw);                 // [query residue][db residue]
+  uint16_t *prof_all = reinterpret_cast<uint16_t *>(smem_raw + 2048);    // per warp [R][32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint16_t *prof = prof_all + warp * (R * 32);
+
+  for (int i = threadIdx.x; i < kAlphabet * kAlphabet; i += blockDim.x) {
+    const int c = i >> 5, q = i & 31;  // matrix[db residue * 32 + query residue] (aligner.cpp:612-618)
+    matT[q * 32 + c] = (int16_t)p.matrix[i];
+  }
+  __syncthreads();
+
+  const int go = p.open_gap, ge = p.extend_gap;
+  const int gef = go > ge ? go : ge;  // F_{k+1} = max(F_k + max(ge,go), m_k + go), see header
+  const uint32_t go_pk = pack2(go), ge_pk = pack2(ge), gef_pk = pack2(gef);
+  const uint32_t total_tasks = p.task_prefix[p.n_q];
+  const uint32_t gwarp = blockIdx.x * kSwWarps + warp;
+  const uint32_t L = p.query_len;
+
+  while (true) {
+    uint32_t task = 0;
+    if (lane == 0) task = atomicAdd(p.task_counter, 1u);
+    task = __shfl_sync(kFull, task, 0);
+    if (task >= total_tasks) break;
+    uint32_t lo = 0, hi = p.n_q;  // task_prefix[lo] <= task < task_prefix[hi]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (p.task_prefix[mid] <= task) lo = mid; else hi = mid;
+    }
+    const uint32_t q = p.first_query + lo;
+    const uint32_t blk = task - p.task_prefix[lo];
+    const uint32_t cnt = p.cand_cnt[q], off = p.cand_off[q];
+    const uint8_t *query = p.queries + (size_t)q * L;
+
+    // the two candidates of this lane
+    const uint32_t ia = blk * kSwCandPerTask + lane, ib = ia + 32;
+    uint32_t wa = 0, wb = 0, offa = 0, offb = 0;
+    if (ia < cnt) {
+      const uint32_t st = p.cand_start[off + ia];
+      offa = st >= p.extend ? st - p.extend : 0u;                       // aligner.cpp:576-579
+      wa = min(p.base_len, p.db_len - offa);                            // aligner.cpp:580-583
+    }
+    if (ib < cnt) {
+      const uint32_t st = p.cand_start[off + ib];
+      offb = st >= p.extend ? st - p.extend : 0u;
+      wb = min(p.base_len, p.db_len - offb);
+    }
+    const uint8_t *pa = p.db + offa, *pb = p.db + offb;
+    const uint32_t wmax = __reduce_max_sync(kFull, wa > wb ? wa : wb);
+
+    uint32_t best = go_pk;           // running max of H+open, per half (max_score = 0)
+    uint32_t enda = 0, endb = 0;     // column of the last maximum (aligner.cpp:650-653)
+
+    for (uint32_t strip = 0; strip < p.n_strips; ++strip) {
+      // ---- per-warp query profile of this strip: T[k][c] = matrix[c][query[row]] - open
+      __syncwarp();
+#pragma unroll 4
+      for (int k = 0; k < R; ++k) {
+        const uint32_t row = strip * R + k;
+        int v = -16384 - go;  // padding rows below the query never score
+        if (row < L) v = (int)matT[(int)query[row] * 32 + lane] - go;
+        prof[k * 32 + lane] = (uint16_t)v;
+      }
+      __syncwarp();
+
+      const bool first_strip = strip == 0, last_strip = strip + 1 == p.n_strips;
+      uint32_t *scr = p.strip_scratch + (size_t)gwarp * p.base_len * 96 + lane;
+
+      uint32_t hgo[R], e[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) { hgo[k] = go_pk; e[k] = 0u; }        // aligner.cpp:587-590
+      uint32_t top_prev = go_pk;      // H+open of the row above the strip, previous column
+      uint32_t ca = wa > 0 ? pa[0] : kSeqEnd, cb = wb > 0 ? pb[0] : kSeqEnd;
+
+      for (uint32_t j = 0; j < wmax; ++j) {
+        // prefetch the next column's residues; columns beyond a window read as SEQUENCE_END
+        const uint32_t na = (j + 1 < wa) ? pa[j + 1] : (uint32_t)kSeqEnd;
+        const uint32_t nb = (j + 1 < wb) ? pb[j + 1] : (uint32_t)kSeqEnd;
+        uint32_t top = go_pk, f = gef_pk, cmax = 0x80008000u;
+        if (!first_strip) {
+          top = scr[(j * 3 + 0) * 32];
+          f = scr[(j * 3 + 1) * 32];
+          cmax = scr[(j * 3 + 2) * 32];
+        }
+        const uint16_t *ta = prof + ca, *tb = prof + cb;
+        // Row k+1's insertion/diagonal part is issued before row k's H is written, so that the
+        // previous column's H+open of row k is dead by then and hgo[k] is updated in place
+        // (no register rotation at the loop back-edge).
+        e[0] = __viaddmax_s16x2(e[0], ge_pk, hgo[0]);                    // aligner.cpp:623-627
+        uint32_t m = __viaddmax_s16x2_relu(                               // :617-620,:629-631
+            top_prev, (uint32_t)tb[0] * 65536u + (uint32_t)ta[0], e[0]);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          uint32_t m_next = 0;
+          if (k + 1 < R) {
+            const uint32_t s = (uint32_t)tb[(k + 1) * 32] * 65536u + (uint32_t)ta[(k + 1) * 32];
+            e[k + 1] = __viaddmax_s16x2(e[k + 1], ge_pk, hgo[k + 1]);
+            m_next = __viaddmax_s16x2_relu(hgo[k], s, e[k + 1]);
+          }
+          const uint32_t mgo = __vadd2(m, go_pk);
+          hgo[k] = __viaddmax_s16x2(f, go_pk, mgo);                      // H = max(m, F)  :641-643
+          f = __viaddmax_s16x2(f, gef_pk, mgo);                          // :634-639
+          cmax = __vmaxs2(cmax, hgo[k]);
+          m = m_next;
+        }
+        const bool xa = ca == kSeqEnd, xb = cb == kSeqEnd;
+        if (__any_sync(kFull, xa | xb)) {                                // aligner.cpp:664-669
+          const uint32_t keep = (xa ? 0u : 0x0000FFFFu) | (xb ? 0u : 0xFFFF0000u);
+          const uint32_t rst = go_pk & ~keep;
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            hgo[k] = (hgo[k] & keep) | rst;
+            e[k] &= keep;
+          }
+          cmax = (cmax & keep) | (0x80008000u & ~keep);
+        }
+        top_prev = top;
+        if (!last_strip) {
+          scr[(j * 3 + 0) * 32] = hgo[R - 1];
+          scr[(j * 3 + 1) * 32] = f;
+          scr[(j * 3 + 2) * 32] = cmax;
+        } else {
+          bool ph, pl;
+          best = __vibmax_s16x2(cmax, best, &ph, &pl);                  // ">=": last maximum wins
+          if (pl) enda = j;
+          if (ph) endb = j;
+        }
+        ca = na;
+        cb = nb;
+      }
+    }
+    if (ia < cnt) {
+      p.cand_score[off + ia] = (uint32_t)((int)(int16_t)(best & 0xFFFFu) - go);
+      p.cand_end[off + ia] = offa + enda;
+    }
+    if (ib < cnt) {
+      p.cand_score[off + ib] = (uint32_t)((int)(int16_t)(best >> 16) - go);
+      p.cand_end[off + ib] = offb + endb;
+    }
+    const unsigned long long cells =
+        (unsigned long long)__reduce_add_sync(kFull, wa + wb) * (unsigned long long)L;
+    if (lane == 0) atomicAdd(p.cells, cells);
+  }
+}
+
+// One thread per candidate, 32-bit scores, DP columns in local memory: the direct form of the
+// reference loop.  Used when the packed s16 kernel's score range check fails (exotic matrices).
+__global__ void __launch_bounds__(128) sw_extend_s32_kernel(const SwParams p) {
+  const uint32_t L = p.query_len;
+  for (uint32_t qi = blockIdx.x; qi < p.n_q; qi += gridDim.x) {
+    const uint32_t q = p.first_query + qi, off = p.cand_off[q], cnt = p.cand_cnt[q];
+    const uint8_t *query = p.queries + (size_t)q * L;
+    for (uint32_t ci = threadIdx.x; ci < cnt; ci += blockDim.x) {
+      const uint32_t i = off + ci;
+      const uint32_t st = p.cand_start[i];
+      const uint32_t dbo = st >= p.extend ? st - p.extend : 0u;
+      const uint32_t w = min(p.base_len, p.db_len - dbo);
+      int h[1024 + 1], ins[1024 + 1];
+      for (uint32_t k = 0; k <= L; ++k) { h[k] = 0; ins[k] = 0; }
+      int best = 0;
+      uint32_t end = 0;
+      for (uint32_t j = 0; j < w; ++j) {
+        const uint8_t c = p.db[dbo + j];
+        if (c != kSeqEnd) {
+          const int32_t *row = p.matrix + c * kAlphabet;
+          int diag = 0, del = 0;
+          for (uint32_t k = 1; k <= L; ++k) {
+            int v = max(0, diag + row[query[k - 1]]);
+            ins[k] = max(ins[k] + p.extend_gap, h[k] + p.open_gap);
+            v = max(v, ins[k]);
+            del = max(del + p.extend_gap, h[k - 1] + p.open_gap);
+            v = max(v, del);
+            diag = h[k];
+            h[k] = v;
+            if (v >= best) { best = v; end = j; }
+          }
+        } else {
+          for (uint32_t k = 0; k <= L; ++k) { h[k] = 0; ins[k] = 0; }
+        }
+      }
+      p.cand_score[i] = (uint32_t)best;
+      p.cand_end[i] = dbo + end;
+      atomicAdd(p.cells, (unsigned long long)w * L);
+    }
+  }
+}
+
+template <int R>
+cudaError_t launch_dpx(const SwParams &p, int sm_count, cudaStream_t stream) {
+  const size_t smem = 2048 + (size_t)kSwWarps * R * 32 * sizeof(uint16_t);
+  cudaError_t err = cudaFuncSetAttribute(sw_extend_dpx_kernel<R>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  sw_extend_dpx_kernel<R><<<sm_count, kSwThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// rows per strip for a query length: the smallest instantiated R that covers L in
+// ceil(L / kSwMaxRows) strips.
+int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips) {
+  static const int kRows[] = {16, 32, 48, 64, 75, 80};
+  const uint32_t strips = (query_len + kSwMaxRows - 1) / kSwMaxRows;
+  const uint32_t need = (query_len + strips - 1) / strips;
+  for (int r : kRows)
+    if ((uint32_t)r >= need) { *n_strips = (query_len + r - 1) / r; return r; }
+  *n_strips = strips;
+  return kSwMaxRows;
+}
+
+cudaError_t sw_extend_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream) {
+  switch (rows) {
+    case 16: return launch_dpx<16>(p, sm_count, stream);
+    case 32: return launch_dpx<32>(p, sm_count, stream);
+    case 48: return launch_dpx<48>(p, sm_count, stream);
+    case 64: return launch_dpx<64>(p, sm_count, stream);
+    case 75: return launch_dpx<75>(p, sm_count, stream);
+    case 80: return launch_dpx<80>(p, sm_count, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t sw_extend_s32_launch(const SwParams &p, int sm_count, cudaStream_t stream) {
+  if (p.query_len > 1024) return cudaErrorInvalidValue;
+  sw_extend_s32_kernel<<<sm_count * 8, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace gm
