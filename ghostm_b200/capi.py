@@ -22,7 +22,9 @@ EXTENDED_SYMBOLS = ["gm_version", "gm_last_error", "gm_device_count", "gm_create
                     "gm_set_options", "gm_set_candidate_capacity", "gm_db_upload", "gm_db_release",
                     "gm_query_upload", "gm_align_chunk", "gm_results_download", "gm_results_upload",
                     "gm_search", "gm_chunk_rule", "gm_candidates_download", "gm_score", "gm_merge",
-                    "gm_db_build_index", "gm_db_download_index"]
+                    "gm_db_build_index", "gm_db_download_index", "gm_results_clear",
+                    "gm_results_device", "gm_stream", "gm_measure_dpx_peak",
+                    "gm_set_deferred_traceback", "gm_traceback_pending"]
 
 HIT_DTYPE = np.dtype([("query_id", "<u4"), ("db_id", "<u4"), ("db_chunk", "<u4"), ("score", "<u4"),
                       ("db_start", "<u4"), ("db_end", "<u4"), ("aln_len", "<u4"),
@@ -88,6 +90,13 @@ def load():
     L.gm_merge.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(GmStats)]
     L.gm_db_build_index.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]
     L.gm_db_download_index.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32)]
+    L.gm_set_deferred_traceback.argtypes = [vp, C.c_int]
+    L.gm_traceback_pending.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(GmStats)]
+    L.gm_results_clear.argtypes = [vp]
+    L.gm_results_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.gm_stream.restype = vp
+    L.gm_stream.argtypes = [vp]
+    L.gm_measure_dpx_peak.argtypes = [vp, C.POINTER(C.c_double)]
     # legacy (reference aligner_gpu.h:32-117)
     L.GetNeededGPUMemorySize.restype = C.c_size_t
     L.GetNeededGPUMemorySize.argtypes = [C.c_uint32] * 6
@@ -226,6 +235,40 @@ class Context:
         counts = np.zeros(self.n_queries, dtype=np.uint32)
         self._check(self.L.gm_results_download(self.h, _ptr(hits), _ptr(counts)))
         return hits, counts
+
+    def set_deferred_traceback(self, on: bool):
+        self._check(self.L.gm_set_deferred_traceback(self.h, int(on)))
+
+    def traceback_pending(self, stats: Optional[GmStats] = None) -> int:
+        n = C.c_uint64()
+        self._check(self.L.gm_traceback_pending(self.h, C.byref(n),
+                                                C.byref(stats) if stats is not None else None))
+        return int(n.value)
+
+    def results_clear(self):
+        self._check(self.L.gm_results_clear(self.h))
+
+    def results_device(self):
+        """-> (hits_ptr, counts_ptr) device addresses of the current hit lists."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self.L.gm_results_device(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def stream(self) -> int:
+        return self.L.gm_stream(self.h)
+
+    def measure_dpx_peak(self) -> float:
+        v = C.c_double()
+        self._check(self.L.gm_measure_dpx_peak(self.h, C.byref(v)))
+        return v.value
+
+    def query_upload_ptr(self, ptr: int, n: int, length: int, name_break_ptr: int = 0):
+        """gm_query_upload from a raw host address (e.g. a pinned torch tensor)."""
+        self._check(self.L.gm_query_upload(self.h, ptr, n, length, name_break_ptr or None))
+        self.n_queries = n
+
+    def results_download_ptr(self, hits_ptr: int, counts_ptr: int):
+        self._check(self.L.gm_results_download(self.h, hits_ptr, counts_ptr))
 
     def results_upload(self, hits: np.ndarray, counts: np.ndarray):
         hits = np.ascontiguousarray(hits, dtype=HIT_DTYPE)

@@ -26,6 +26,9 @@ cudaError_t merge_launch(const MergeParams &p, int sm_count, cudaStream_t stream
 int traceback_grid(int sm_count);
 int traceback_threads();
 cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_t stream);
+cudaError_t collect_pending_launch(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
+                                   uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
+                                   uint32_t *n_jobs, int sm_count, cudaStream_t stream);
 
 namespace {
 
@@ -219,6 +222,11 @@ struct gm_context {
   DevBuf<uint32_t> jobs;
   DevBuf<unsigned long long> big_scratch;
   DevBuf<int> tb_work;
+  DevBuf<ChunkRef> chunk_tab;
+  bool chunk_tab_dirty = true;
+  bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
+  bool pending = false;      // some resident hit list may hold untraced hits
+  uint32_t serial = 0;
 };
 
 namespace {
@@ -316,7 +324,7 @@ extern "C" void gm_destroy(gm_context *c) {
   c->cand_end.release(); c->staging.release(); c->prefix.release(); c->gather0.release();
   c->gather1.release(); c->gather2.release(); c->strip_scratch.release(); c->counters.release();
   c->small.release(); c->hits[0].release(); c->hits[1].release(); c->hit_cnt[0].release();
-  c->hit_cnt[1].release(); c->jobs.release(); c->big_scratch.release(); c->tb_work.release();
+  c->hit_cnt[1].release(); c->jobs.release(); c->big_scratch.release(); c->tb_work.release(); c->chunk_tab.release();
   for (auto &e : c->ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -388,6 +396,7 @@ extern "C" int gm_db_upload(gm_context *c, uint32_t id, const uint8_t *seq, uint
   ch.positions_len = positions_len;
   ch.n_seqs = n_seqs;
   ch.valid = true;
+  c->chunk_tab_dirty = true;
   if (c->cur_chunk == (int)id) c->cur_chunk = -1;
   return 0;
 }
@@ -399,6 +408,7 @@ extern "C" int gm_db_release(gm_context *c, uint32_t id) {
   GM_CUDA(cudaStreamSynchronize(c->stream));
   ch.seq.release(); ch.keys_count.release(); ch.positions.release(); ch.seq_starts.release();
   ch.valid = false;
+  c->chunk_tab_dirty = true;
   if (c->cur_chunk == (int)id) c->cur_chunk = -1;
   return 0;
 }
@@ -441,6 +451,7 @@ extern "C" int gm_query_upload(gm_context *c, const uint8_t *seqs, uint32_t n, u
   c->cur_hits = 0;
   c->cur_chunk = -1;
   c->cand_total = 0;
+  c->pending = false;
   return 0;
 }
 
@@ -668,6 +679,79 @@ extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *s
   return 0;
 }
 
+namespace {
+
+int sync_chunk_tab(gm_context *c) {
+  if (!c->chunk_tab_dirty) return 0;
+  std::vector<ChunkRef> tab(GM_MAX_DB_CHUNKS);
+  for (int i = 0; i < GM_MAX_DB_CHUNKS; ++i) {
+    tab[i].seq = c->chunks[i].valid ? c->chunks[i].seq.p : nullptr;
+    tab[i].seq_starts = c->chunks[i].valid ? c->chunks[i].seq_starts.p : nullptr;
+  }
+  GM_CUDA(c->chunk_tab.ensure(GM_MAX_DB_CHUNKS));
+  GM_CUDA(cudaMemcpyAsync(c->chunk_tab.p, tab.data(), tab.size() * sizeof(ChunkRef),
+                          cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  c->chunk_tab_dirty = false;
+  return 0;
+}
+
+// TraceBack of the jobs queued in c->jobs / small[3] on the hit lists `hits`.
+int run_traceback(gm_context *c, gm_hit *hits) {
+  if (int r = sync_chunk_tab(c)) return r;
+  TracebackParams t = {};
+  t.queries = c->queries.p;
+  t.query_len = c->query_len;
+  t.chunks = c->chunk_tab.p;
+  t.hits = hits;
+  t.jobs = c->jobs.p;
+  t.n_jobs = c->small.p + 3;
+  t.matrix = c->matrix.p;
+  t.open_gap = c->opt.open_gap;
+  t.extend_gap = c->opt.extend_gap;
+  t.base_len = c->query_len + 2 * c->opt.extend * 2 * (1u << c->opt.log_region);  // aligner.cpp:775
+  const size_t tb_threads = (size_t)traceback_grid(c->sm_count) * traceback_threads();
+  GM_CUDA(c->tb_work.ensure(tb_threads * 4 * (c->query_len + 1)));
+  t.work = c->tb_work.p;
+  GM_CUDA(traceback_launch(t, c->sm_count, c->stream));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int gm_set_deferred_traceback(gm_context *c, int on) {
+  if (int r = check_ctx(c)) return r;
+  if (c->pending) return fail(GM_ERR_ARGUMENT, "pending tracebacks: call gm_traceback_pending first");
+  c->deferred = on != 0;
+  return 0;
+}
+
+extern "C" int gm_traceback_pending(gm_context *c, uint64_t *n_done, gm_stats *stats) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  if (int r = sync_chunk_tab(c)) return r;
+  gm_hit *hits = c->hits[c->cur_hits].p;
+  GM_CUDA(cudaMemsetAsync(c->small.p + 3, 0, 4, c->stream));
+  GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  GM_CUDA(collect_pending_launch(hits, c->hit_cnt[c->cur_hits].p, c->n_queries, c->cap,
+                                 c->chunk_tab.p, c->jobs.p, c->small.p + 3, c->sm_count, c->stream));
+  if (int r = run_traceback(c, hits)) return r;
+  GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  uint32_t n = 0;
+  GM_CUDA(cudaMemcpyAsync(&n, c->small.p + 3, 4, cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  c->pending = false;
+  if (n_done) *n_done = n;
+  if (stats) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    stats->ms_traceback += ms;
+    stats->tracebacks += n;
+    stats->kernel_launches += 2;
+  }
+  return 0;
+}
+
 extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *stats) {
   if (int r = check_ctx(c)) return r;
   if (int r = check_range(c, first, end)) return r;
@@ -710,28 +794,20 @@ extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *s
   p.error = reinterpret_cast<int *>(c->small.p + 4);
   p.run_counter = c->small.p + 5;
   p.smem_elems = 1536;
+  p.serial = ++c->serial;
+  if (p.serial == kNoId) p.serial = c->serial = 1;
+  p.deferred = c->deferred ? 1 : 0;
   GM_CUDA(cudaMemsetAsync(c->small.p + 3, 0, 3 * 4, c->stream));
   GM_CUDA(cudaMemsetAsync(c->counters.p + 3, 0, 8, c->stream));
   GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
   GM_CUDA(merge_launch(p, c->sm_count, c->stream));
   GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
 
-  TracebackParams t = {};
-  t.queries = c->queries.p;
-  t.query_len = c->query_len;
-  t.db = ch.seq.p;
-  t.seq_starts = ch.seq_starts.p;
-  t.hits = c->hits[dst].p;
-  t.jobs = c->jobs.p;
-  t.n_jobs = c->small.p + 3;
-  t.matrix = c->matrix.p;
-  t.open_gap = c->opt.open_gap;
-  t.extend_gap = c->opt.extend_gap;
-  t.base_len = c->query_len + 2 * c->opt.extend * 2 * (1u << c->opt.log_region);  // aligner.cpp:775
-  const size_t tb_threads = (size_t)traceback_grid(c->sm_count) * traceback_threads();
-  GM_CUDA(c->tb_work.ensure(tb_threads * 4 * (c->query_len + 1)));
-  t.work = c->tb_work.p;
-  GM_CUDA(traceback_launch(t, c->sm_count, c->stream));
+  if (!c->deferred) {
+    if (int r = run_traceback(c, c->hits[dst].p)) return r;
+  } else {
+    c->pending = true;
+  }
   GM_CUDA(cudaEventRecord(c->ev[2], c->stream));
   uint32_t small[8];
   GM_CUDA(cudaMemcpyAsync(small, c->small.p, sizeof(small), cudaMemcpyDeviceToHost, c->stream));
@@ -744,8 +820,8 @@ extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *s
     stats->ms_merge += ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
     stats->ms_traceback += ms;
-    stats->tracebacks += small[3];
-    stats->kernel_launches += 2;
+    if (!c->deferred) stats->tracebacks += small[3];
+    stats->kernel_launches += c->deferred ? 1 : 2;
     stats->candidate_chunks += 1;
   }
   return 0;
@@ -772,6 +848,8 @@ extern "C" int gm_align_chunk(gm_context *c, uint32_t id, gm_stats *stats) {
 extern "C" int gm_results_download(gm_context *c, gm_hit *hits, uint32_t *counts) {
   if (int r = check_ctx(c)) return r;
   if (int r = ensure_query_state(c)) return r;
+  if (c->pending)
+    if (int r = gm_traceback_pending(c, nullptr, nullptr)) return r;
   if (hits)
     GM_CUDA(cudaMemcpyAsync(hits, c->hits[c->cur_hits].p, (size_t)c->n_queries * c->cap * sizeof(gm_hit),
                             cudaMemcpyDeviceToHost, c->stream));
@@ -791,6 +869,65 @@ extern "C" int gm_results_upload(gm_context *c, const gm_hit *hits, const uint32
   GM_CUDA(cudaMemcpyAsync(c->hit_cnt[c->cur_hits].p, counts, (size_t)c->n_queries * 4,
                           cudaMemcpyHostToDevice, c->stream));
   GM_CUDA(cudaStreamSynchronize(c->stream));
+  c->pending = true;  // uploaded lists may carry untraced hits of chunks resident here
+  return 0;
+}
+
+extern "C" int gm_results_clear(gm_context *c) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  GM_CUDA(cudaMemsetAsync(c->hit_cnt[c->cur_hits].p, 0, (size_t)c->n_queries * 4, c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gm_results_device(gm_context *c, void **hits, void **counts) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  if (hits) *hits = c->hits[c->cur_hits].p;
+  if (counts) *counts = c->hit_cnt[c->cur_hits].p;
+  return 0;
+}
+
+extern "C" void *gm_stream(gm_context *c) { return c ? (void *)c->stream : nullptr; }
+
+namespace gm_peak {
+__global__ void __launch_bounds__(1024) dpx_peak_kernel(uint32_t *out, uint32_t a, uint32_t b, int iters) {
+  uint32_t acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x * 2654435761u + i * b;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = __viaddmax_s16x2(acc[i], a, b);
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r ^= acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+}  // namespace gm_peak
+
+extern "C" int gm_measure_dpx_peak(gm_context *c, double *lane_instr_per_s) {
+  if (int r = check_ctx(c)) return r;
+  if (!lane_instr_per_s) return fail(GM_ERR_ARGUMENT, "null output");
+  DevBuf<uint32_t> out;
+  GM_CUDA(out.ensure((size_t)c->sm_count * 1024));
+  const int iters = 1 << 15;
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    GM_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    gm_peak::dpx_peak_kernel<<<c->sm_count, 1024, 0, c->stream>>>(out.p, 3u, 0x00050007u, iters);
+    GM_CUDA(cudaGetLastError());
+    GM_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    GM_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    GM_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]));
+    const double rate = (double)iters * 8 * 1024 * c->sm_count / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  out.release();
+  *lane_instr_per_s = best;
   return 0;
 }
 
@@ -837,6 +974,7 @@ extern "C" int gm_db_build_index(gm_context *c, uint32_t id, const uint8_t *seq,
   ch.keys_count_len = n_keys + 1;
   ch.positions_len = n_pos;
   ch.valid = true;
+  c->chunk_tab_dirty = true;
   if (c->cur_chunk == (int)id) c->cur_chunk = -1;
   return 0;
 }

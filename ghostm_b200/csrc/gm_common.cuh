@@ -96,13 +96,21 @@ struct MergeParams {
   int *error;                  // set on scratch exhaustion
   uint32_t *run_counter;
   uint32_t smem_elems;         // list capacity per warp in shared memory (u32 records)
+  uint32_t serial;             // id of this Merge call: marks hits accepted by it
+  int deferred;                // 1: TraceBack runs later on the survivors (no job queue here)
+};
+
+// A hit whose TraceBack has not run yet carries aln_match == kNoId, aln_len == serial of the
+// Merge call that accepted it, db_start == candidate region start and the ABSOLUTE db_end.
+struct ChunkRef {
+  const uint8_t *seq;
+  const uint32_t *seq_starts;
 };
 
 struct TracebackParams {
   const uint8_t *queries;
   uint32_t query_len;
-  const uint8_t *db;
-  const uint32_t *seq_starts;
+  const ChunkRef *chunks;      // [GM_MAX_DB_CHUNKS]; seq == nullptr: chunk not resident here
   gm_hit *hits;
   const uint32_t *jobs;
   const uint32_t *n_jobs;

@@ -249,7 +249,8 @@ __device__ void merge_run(const MergeParams &p, Rec *list, uint32_t n_new, uint3
         const uint32_t db_id = db_get_id(p.seq_starts, p.n_seqs, p.db_len, end);
         bool seen = false;  // overlap[db_id] == id (aligner.cpp:707): accepted earlier in this call
         for (uint32_t k = 0; k < out && k < p.cap; ++k)
-          seen |= dst[k].db_chunk == p.db_chunk && dst[k].db_id == db_id && dst[k].aln_len == kNoId;
+          seen |= dst[k].db_chunk == p.db_chunk && dst[k].db_id == db_id &&
+                  dst[k].aln_match == kNoId && dst[k].aln_len == p.serial;
         if (!seen) {
           if (out < p.cap) {
             gm_hit h;
@@ -259,11 +260,11 @@ __device__ void merge_run(const MergeParams &p, Rec *list, uint32_t n_new, uint3
             h.score = p.cand_score[g];
             h.db_start = p.cand_start[g];
             h.db_end = end;          // absolute; TraceBack makes both sequence-relative
-            h.aln_len = kNoId;       // marks "new in this call, traceback pending"
-            h.aln_match = kNoId;
+            h.aln_len = p.serial;    // accepted by this call ...
+            h.aln_match = kNoId;     // ... TraceBack pending
             h.seq_id = 0.f;
             dst[out] = h;
-            p.jobs[atomicAdd(p.n_jobs, 1u)] = ql * p.cap + out;
+            if (!p.deferred) p.jobs[atomicAdd(p.n_jobs, 1u)] = ql * p.cap + out;
           }
           ++out;
         }
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TracebackParams p)
 #define GM_COL(a, k) dp[((size_t)(a) * (L + 1) + (k)) * stride]
   for (uint32_t job = tid; job < n_jobs; job += stride) {
     gm_hit h = p.hits[p.jobs[job]];
+    const ChunkRef chunk = p.chunks[h.db_chunk];
     const uint8_t *query = p.queries + (size_t)h.query_id * L;
     const uint32_t db_offset = h.db_end;
     uint32_t len = p.base_len;
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TracebackParams p)
     int max_score = 0;
     uint32_t max_start = 0, max_match = 0, max_len = 0;
     for (uint32_t j = 0; j < len; ++j) {
-      const uint8_t c = p.db[db_offset - j];
+      const uint8_t c = chunk.seq[db_offset - j];
       if (c == kSeqEnd) break;                                        // aligner.cpp:927-929
       const int32_t *row = p.matrix + c * kAlphabet;
       int temp_score = 0, del = 0;
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TracebackParams p)
         }
       }
     }
-    const uint32_t seq_pos = p.seq_starts[h.db_id];
+    const uint32_t seq_pos = chunk.seq_starts[h.db_id];
     h.db_start = db_offset - max_start - seq_pos;                     // aligner.cpp:941, :715
     h.db_end = db_offset - seq_pos;                                   // :716
     h.seq_id = (float)max_match / (float)(int)max_len;                // :945
@@ -388,7 +390,29 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TracebackParams p)
 #undef GM_COL
 }
 
+// Collect the result slots whose TraceBack is pending and whose db chunk is resident here.
+__global__ void collect_pending_kernel(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
+                                       uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
+                                       uint32_t *n_jobs) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_queries * cap;
+       i += gridDim.x * blockDim.x) {
+    const uint32_t q = i / cap, k = i - q * cap;
+    if (k >= counts[q]) continue;
+    const gm_hit &h = hits[i];
+    if (h.aln_match == kNoId && h.db_chunk < GM_MAX_DB_CHUNKS && chunks[h.db_chunk].seq != nullptr)
+      jobs[atomicAdd(n_jobs, 1u)] = i;
+  }
+}
+
 }  // namespace
+
+cudaError_t collect_pending_launch(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
+                                   uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
+                                   uint32_t *n_jobs, int sm_count, cudaStream_t stream) {
+  collect_pending_kernel<<<sm_count * 4, 256, 0, stream>>>(hits, counts, n_queries, cap, chunks, jobs,
+                                                           n_jobs);
+  return cudaGetLastError();
+}
 
 size_t merge_smem_bytes(uint32_t elems_per_warp) { return (size_t)kMergeWarps * elems_per_warp * 4; }
 

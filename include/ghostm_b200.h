@@ -172,6 +172,26 @@ int gm_results_download(gm_context *ctx, gm_hit *hits, uint32_t *counts);
 /* Replace the device hit lists (used to hand carried lists from one GPU to the next). */
 int gm_results_upload(gm_context *ctx, const gm_hit *hits, const uint32_t *counts);
 
+/* TraceBack scheduling.  Selection in Merge never reads TraceBack's output (the dedupe key is
+ * DB::GetID of the forward end, aligner.cpp:706-709), so by default (on = 1) TraceBack is
+ * deferred: hits stay "pending" (absolute db_end, aln_match == 0xFFFFFFFF) until
+ * gm_traceback_pending runs it once for the survivors whose db chunk is resident in this
+ * context.  gm_results_download calls it implicitly.  on = 0 restores the reference order
+ * (TraceBack inside every Merge). */
+int gm_set_deferred_traceback(gm_context *ctx, int on);
+int gm_traceback_pending(gm_context *ctx, uint64_t *n_done, gm_stats *stats);
+/* Empty the device hit lists without re-uploading the queries. */
+int gm_results_clear(gm_context *ctx);
+/* Device addresses of the current hit lists (gm_hit[n_queries][cap], uint32[n_queries]) for
+ * peer-to-peer exchange between GPUs (NCCL send/recv on these buffers); valid until the next
+ * gm_merge / gm_align_chunk / gm_query_upload. */
+int gm_results_device(gm_context *ctx, void **hits, void **counts);
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on. */
+void *gm_stream(gm_context *ctx);
+/* INT/DPX issue-rate roofline: runs a register-only VIADDMNMX.S16x2 loop on every SM and
+ * returns lane-instructions per second (x4 = packed add+max operations per second). */
+int gm_measure_dpx_peak(gm_context *ctx, double *lane_instr_per_s);
+
 /* ---- stage level (parity tests, the legacy symbols, multi-GPU drivers) ---- */
 
 /* Seed search of all resident queries against chunk_id: per-query candidate counts and the

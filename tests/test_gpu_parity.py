@@ -33,12 +33,15 @@ def test_stage_parity(gpu_ctx, name):
     assert n_stages > 0
 
 
+@pytest.mark.parametrize("deferred", [True, False])
 @pytest.mark.parametrize("name", WORKLOADS)
-def test_hit_lists(gpu_ctx, name):
-    """Final hit lists (Merge + TraceBack on the device) and the formatted output text."""
+def test_hit_lists(gpu_ctx, name, deferred):
+    """Final hit lists (Merge + TraceBack on the device), with TraceBack deferred to the
+    survivors (default) and in the reference order (inside every Merge)."""
     db, qchunks, kw = H.workload(name)
     opt = O.Options(**kw)
     H.setup_context(gpu_ctx, db, opt)
+    gpu_ctx.set_deferred_traceback(deferred)
     for qc in qchunks:
         ref = O.align_chunk(qc, db, opt)
         gpu_ctx.query_upload(qc.seqs, qc.name_breaks())
@@ -50,3 +53,4 @@ def test_hit_lists(gpu_ctx, name):
             ok, field = H.hits_equal(hits[i, :counts[i]], ref.hits[i, :counts[i]])
             assert ok, (name, i, field, hits[i, :counts[i]], ref.hits[i, :counts[i]])
     assert int(ref.counts.sum()) > 0
+    gpu_ctx.set_deferred_traceback(True)
