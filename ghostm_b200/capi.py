@@ -24,7 +24,7 @@ EXTENDED_SYMBOLS = ["gm_version", "gm_last_error", "gm_device_count", "gm_create
                     "gm_search", "gm_chunk_rule", "gm_candidates_download", "gm_score", "gm_merge",
                     "gm_db_build_index", "gm_db_download_index", "gm_results_clear",
                     "gm_results_device", "gm_stream", "gm_measure_dpx_peak",
-                    "gm_set_deferred_traceback", "gm_traceback_pending"]
+                    "gm_set_deferred_traceback", "gm_traceback_pending", "gm_set_search_variant"]
 
 HIT_DTYPE = np.dtype([("query_id", "<u4"), ("db_id", "<u4"), ("db_chunk", "<u4"), ("score", "<u4"),
                       ("db_start", "<u4"), ("db_end", "<u4"), ("aln_len", "<u4"),
@@ -91,6 +91,7 @@ def load():
     L.gm_db_build_index.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]
     L.gm_db_download_index.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32)]
     L.gm_set_deferred_traceback.argtypes = [vp, C.c_int]
+    L.gm_set_search_variant.argtypes = [vp, C.c_int]
     L.gm_traceback_pending.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(GmStats)]
     L.gm_results_clear.argtypes = [vp]
     L.gm_results_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
@@ -235,6 +236,9 @@ class Context:
         counts = np.zeros(self.n_queries, dtype=np.uint32)
         self._check(self.L.gm_results_download(self.h, _ptr(hits), _ptr(counts)))
         return hits, counts
+
+    def set_search_variant(self, fast: bool):
+        self._check(self.L.gm_set_search_variant(self.h, int(fast)))
 
     def set_deferred_traceback(self, on: bool):
         self._check(self.L.gm_set_deferred_traceback(self.h, int(on)))

@@ -18,7 +18,7 @@ int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips);
 cudaError_t sw_extend_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream);
 cudaError_t sw_extend_s32_launch(const SwParams &p, int sm_count, cudaStream_t stream);
 uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions);
-cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream);
+cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream, bool allow_fast);
 int search_max_list_len();
 int search_max_threshold();
 size_t merge_smem_bytes(uint32_t elems_per_warp);
@@ -224,6 +224,7 @@ struct gm_context {
   DevBuf<int> tb_work;
   DevBuf<ChunkRef> chunk_tab;
   bool chunk_tab_dirty = true;
+  bool search_fast = true;   // register-window search kernel when the options allow it
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits
   uint32_t serial = 0;
@@ -500,8 +501,9 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     p.query_counter = c->small.p + 0;
     p.positions_visited = c->counters.p + 1;
     p.overflow = reinterpret_cast<int *>(c->small.p + 2);
+    p.debug = getenv("GM_SEARCH_DEBUG") ? (uint32_t)atoi(getenv("GM_SEARCH_DEBUG")) : 0u;
     GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    GM_CUDA(seed_search_launch(p, grid, c->stream));
+    GM_CUDA(seed_search_launch(p, grid, c->stream, c->search_fast));
     GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
     GM_CUDA(cudaMemcpyAsync(c->h_counts.data(), c->cand_cnt.p, (size_t)c->n_queries * 4,
                             cudaMemcpyDeviceToHost, c->stream));
@@ -718,6 +720,12 @@ int run_traceback(gm_context *c, gm_hit *hits) {
 }
 
 }  // namespace
+
+extern "C" int gm_set_search_variant(gm_context *c, int fast) {
+  if (int r = check_ctx(c)) return r;
+  c->search_fast = fast != 0;
+  return 0;
+}
 
 extern "C" int gm_set_deferred_traceback(gm_context *c, int on) {
   if (int r = check_ctx(c)) return r;

@@ -62,6 +62,7 @@ struct SearchParams {
   uint32_t *query_counter;     // dynamic query fetch
   unsigned long long *positions_visited;
   int *overflow;               // set when cand_capacity is exceeded
+  uint32_t debug;              // timing experiments only (GM_SEARCH_DEBUG), 0 in production
 };
 
 // ---- merge / traceback --------------------------------------------------------------

@@ -247,6 +247,327 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_kernel(const Se
   if (tid == 0 && sh.visited) atomicAdd(p.positions_visited, sh.visited);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path (list_len <= 64): same bit-plane tiles and the same three passes, reorganised so
+// that the work is balanced and the passes run out of registers.
+//   * slice boundaries: for a batch of kTileBatch tiles, thread (list j, boundary t) finds by
+//     binary search the first index of list j whose region is >= the tile base (the lists are
+//     sorted, so every tile's slice of every list is a contiguous index range);
+//   * balanced chunks: a tile's work is the concatenation of its slices cut into 32-position
+//     chunks; chunk k goes to warp k % 32, whichever list it belongs to, so skewed k-mer
+//     frequencies (one list with thousands of positions, others with a handful) do not leave
+//     warps idle at the barriers;
+//   * a warp keeps the mark index of its (up to kSlots) chunks in registers across the three
+//     passes and loads the next tile's chunks right after computing the current marks, so the
+//     HBM latency of the next tile hides behind the passes of the current one;
+//   * per tile 3 block barriers; ordered compaction of the sparse emit bitmap by one warp.
+constexpr int kTileBatch = 16;
+constexpr int kSlots = 8;                // register-resident chunks per warp per tile
+constexpr int kFastLists = 64;
+constexpr int kChunk = 31;               // new positions per chunk (lane 0 carries the predecessor)
+constexpr int kChunkTable = kSlots * kSearchWarps;   // chunks per tile with a list-id table entry
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+struct FastShared {
+  uint32_t lbeg[kFastLists], lend[kFastLists];
+  uint32_t bnd[kTileBatch + 1][kFastLists];       // first index with region >= base of tile t
+  uint32_t fr[kTileBatch + 1][kFastLists];        // region of that position (kNone: none left)
+  uint32_t pre[kTileBatch][kFastLists + 1];       // exclusive prefix of chunks per list
+  uint8_t chunk_list[kTileBatch][kChunkTable];    // chunk k -> list (k < kChunkTable)
+  uint32_t scan[kSearchWarps];
+  uint32_t min_d, max_d;
+  uint32_t query, out_n;
+  unsigned long long base;
+  unsigned long long visited;
+};
+
+// list of chunk k of tile t
+__device__ __forceinline__ uint32_t chunk_to_list(const SearchParams &p, const FastShared &sh, int t,
+                                                  uint32_t k, uint32_t lane) {
+  if (k < kChunkTable) return sh.chunk_list[t][k];
+  const uint32_t *pre = sh.pre[t];   // rare: very dense tile, search the prefix table
+  const bool hit0 = lane < p.list_len && pre[lane] <= k && k < pre[lane + 1];
+  const bool hit1 = lane + 32 < p.list_len && pre[lane + 32] <= k && k < pre[lane + 33];
+  const uint32_t b0 = __ballot_sync(kFull, hit0), b1 = __ballot_sync(kFull, hit1);
+  return b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
+}
+
+// Lane l > 0 of chunk k holds position (slice start + 31*(k - pre[j]) + l - 1); lane 0 holds the
+// position before the chunk (kNone for the first chunk of a slice), so that "first position of a
+// (list, region) run" is a plain compare with the left neighbour lane.
+__device__ __forceinline__ uint32_t load_chunk(const SearchParams &p, const FastShared &sh, int t,
+                                               uint32_t k, uint32_t lane) {
+  const uint32_t j = chunk_to_list(p, sh, t, k, lane);
+  const uint32_t c = k - sh.pre[t][j];
+  const uint32_t idx = sh.bnd[t][j] + kChunk * c + lane - 1;
+  const bool ok = (lane > 0 || c > 0) && idx < sh.bnd[t + 1][j];
+  return ok ? __ldg(p.positions + idx) : kNone;
+}
+
+// mark index (region - base) of a loaded chunk element, kNone unless it starts a run
+__device__ __forceinline__ uint32_t chunk_mark(const SearchParams &p, const FastShared &sh, int t,
+                                               uint32_t k, uint32_t lane, uint32_t pos, uint32_t base) {
+  const uint32_t off = chunk_to_list(p, sh, t, k, lane) * p.shift;
+  const uint32_t d = pos != kNone ? (pos - off) >> p.log_region : kNone;
+  const uint32_t dprev = __shfl_up_sync(kFull, d, 1);
+  return (lane > 0 && pos != kNone && d != dprev) ? d - base : kNone;
+}
+
+template <int T>
+__device__ __forceinline__ void arrive(uint32_t *planes, uint32_t words, uint32_t x) {
+  const uint32_t w = x >> 5, bit = 1u << (x & 31);
+  uint32_t old = atomicOr(&planes[w], bit);
+#pragma unroll
+  for (int tt = 1; tt < T; ++tt)
+    if (old & bit) old = atomicOr(&planes[tt * words + w], bit); else break;
+}
+
+template <int T>
+__global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(const SearchParams p) {
+  extern __shared__ __align__(16) uint32_t dyn[];
+  __shared__ FastShared sh;
+  const uint32_t M = p.tile_regions;
+  const uint32_t words = M / 32 + 1;
+  uint32_t *planes = dyn;
+  uint32_t *emitb = dyn + T * words;
+  uint32_t *summary = emitb + words;
+  const uint32_t groups = M / 1024;
+  const uint32_t n_sw = (groups + 31) / 32;       // <= 32 summary words, one per warp
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t *staging = p.staging + (size_t)blockIdx.x * p.staging_cap;
+  const uint32_t r = p.log_region;
+
+  for (uint32_t i = tid; i < (T + 1) * words + groups / 32 + 1; i += kSearchThreads) dyn[i] = 0;
+  if (tid == 0) sh.visited = 0;
+  __syncthreads();
+
+  while (true) {
+    if (tid == 0) sh.query = atomicAdd(p.query_counter, 1u);
+    __syncthreads();
+    const uint32_t q = sh.query;
+    if (q >= p.n_queries) break;
+    const uint8_t *query = p.queries + (size_t)q * p.query_len;
+
+    uint32_t *out = staging;
+    uint32_t out_cap = p.staging_cap;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      if (tid == 0) { sh.min_d = kNone; sh.max_d = 0; sh.out_n = 0; }
+      __syncthreads();
+      if (tid < p.list_len) {
+        const uint32_t j = tid, off = j * p.shift;
+        const uint32_t key = get_key(query + off, p.seed);
+        uint32_t b = p.keys_count[key];
+        const uint32_t e = p.keys_count[key + 1];                       // index.h:105-114
+        while (b < e && p.positions[b] < off) ++b;                      // aligner.cpp:430-431
+        sh.lbeg[j] = b;
+        sh.lend[j] = e;
+        if (b < e) {
+          atomicMin(&sh.min_d, (p.positions[b] - off) >> r);
+          atomicMax(&sh.max_d, (p.positions[e - 1] - off) >> r);
+          if (attempt == 0) atomicAdd(&sh.visited, (unsigned long long)(e - b));
+        }
+      }
+      __syncthreads();
+      const uint32_t min_d = sh.min_d, max_d = sh.max_d;
+
+      if (min_d != kNone) {
+        const uint32_t tile_first = min_d / M, tile_last = max_d / M;
+        for (uint32_t batch0 = tile_first; batch0 <= tile_last; batch0 += kTileBatch) {
+          const uint32_t n_tiles = min((uint32_t)kTileBatch, tile_last - batch0 + 1);
+          // ---- slice boundaries of this batch: binary search per (list, boundary)
+          for (uint32_t i = tid; i < (n_tiles + 1) * p.list_len; i += kSearchThreads) {
+            const uint32_t t = i / p.list_len, j = i - t * p.list_len;
+            const uint32_t off = j * p.shift;
+            const unsigned long long target = (unsigned long long)(batch0 + t) * M;  // region
+            uint32_t lo = sh.lbeg[j], hi = sh.lend[j];
+            while (lo < hi) {  // first index whose region >= target
+              const uint32_t mid = (lo + hi) >> 1;
+              if ((unsigned long long)((__ldg(p.positions + mid) - off) >> r) < target) lo = mid + 1;
+              else hi = mid;
+            }
+            sh.bnd[t][j] = lo;
+            sh.fr[t][j] = lo < sh.lend[j] ? (__ldg(p.positions + lo) - off) >> r : kNone;
+          }
+          __syncthreads();
+          if (tid < n_tiles) {
+            uint32_t acc = 0;
+            for (uint32_t j = 0; j < p.list_len; ++j) {
+              sh.pre[tid][j] = acc;
+              acc += (sh.bnd[tid + 1][j] - sh.bnd[tid][j] + kChunk - 1) / kChunk;
+            }
+            sh.pre[tid][p.list_len] = acc;
+          }
+          __syncthreads();
+          for (uint32_t i = tid; i < n_tiles * p.list_len; i += kSearchThreads) {
+            const uint32_t t = i / p.list_len, j = i - t * p.list_len;
+            const uint32_t k1 = min(sh.pre[t][j + 1], (uint32_t)kChunkTable);
+            for (uint32_t k = sh.pre[t][j]; k < k1; ++k) sh.chunk_list[t][k] = (uint8_t)j;
+          }
+          __syncthreads();
+
+          // ---- first non-empty tile of the batch: load its chunks
+          uint32_t t = 0;
+          while (t < n_tiles && sh.pre[t][p.list_len] == 0) ++t;
+          uint32_t nxt[kSlots];
+          if (t < n_tiles) {
+            const uint32_t total = sh.pre[t][p.list_len];
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+              const uint32_t k = warp + 32 * s;
+              nxt[s] = k < total ? load_chunk(p, sh, t, k, lane) : kNone;
+            }
+          }
+          while (t < n_tiles) {
+            const uint32_t base = (batch0 + t) * M;
+            const uint32_t total = sh.pre[t][p.list_len];
+            // ---- marks of this tile (run starts), from the loaded chunks
+            uint32_t mark[kSlots];
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+              const uint32_t k = warp + 32 * s;
+              mark[s] = k < total ? chunk_mark(p, sh, t, k, lane, nxt[s], base) : kNone;
+            }
+            // ---- next non-empty tile: issue its loads now (latency hides behind the passes)
+            uint32_t tn = t + 1;
+            while (tn < n_tiles && sh.pre[tn][p.list_len] == 0) ++tn;
+            if (tn < n_tiles) {
+              const uint32_t total_n = sh.pre[tn][p.list_len];
+#pragma unroll
+              for (int s = 0; s < kSlots; ++s) {
+                const uint32_t k = warp + 32 * s;
+                nxt[s] = k < total_n ? load_chunk(p, sh, tn, k, lane) : kNone;
+              }
+            }
+            // ---- pass 1: arrive
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s)
+              if (mark[s] != kNone) arrive<T>(planes, words, mark[s]);
+            // chunks beyond the register slots (very dense tiles): streamed, re-read per pass
+            for (uint32_t k = warp + 32 * kSlots; k < total; k += 32) {
+              const uint32_t x = chunk_mark(p, sh, t, k, lane, load_chunk(p, sh, t, k, lane), base);
+              if (x != kNone) arrive<T>(planes, words, x);
+            }
+            // halo: the first position of region base+M of every list counts for region base+M-1
+            if (tid < p.list_len && sh.fr[t + 1][tid] == base + M) arrive<T>(planes, words, M);
+            __syncthreads();  // A
+            if (tid == 0 && batch0 + t == 0) {
+              // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an
+              // unoccupied region 0 still emits when region 1 alone reaches the threshold.
+              if (!(planes[0] & 1u) && (planes[(T - 1) * words] & 2u)) {
+                atomicOr(&emitb[0], 1u);
+                atomicOr(&summary[0], 1u);
+              }
+            }
+            // ---- pass 2: decide
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+              const uint32_t x = mark[s];
+              if (x != kNone && emits<T>(planes, words, x)) {
+                const uint32_t w = x >> 5;
+                atomicOr(&emitb[w], 1u << (x & 31));
+                atomicOr(&summary[w >> 10], 1u << ((w >> 5) & 31));
+              }
+            }
+            for (uint32_t k = warp + 32 * kSlots; k < total; k += 32) {
+              const uint32_t x = chunk_mark(p, sh, t, k, lane, load_chunk(p, sh, t, k, lane), base);
+              if (x != kNone && emits<T>(planes, words, x)) {
+                const uint32_t w = x >> 5;
+                atomicOr(&emitb[w], 1u << (x & 31));
+                atomicOr(&summary[w >> 10], 1u << ((w >> 5) & 31));
+              }
+            }
+            __syncthreads();  // B
+            // ---- pass 3: clear; compaction step 1: every warp counts the emit bits of the
+            // groups of "its" summary word
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+              const uint32_t x = mark[s];
+              if (x != kNone) {
+#pragma unroll
+                for (int tt = 0; tt < T; ++tt) planes[tt * words + (x >> 5)] = 0;
+              }
+            }
+            for (uint32_t k = warp + 32 * kSlots; k < total; k += 32) {
+              const uint32_t x = chunk_mark(p, sh, t, k, lane, load_chunk(p, sh, t, k, lane), base);
+              if (x != kNone) {
+#pragma unroll
+                for (int tt = 0; tt < T; ++tt) planes[tt * words + (x >> 5)] = 0;
+              }
+            }
+            if (tid < T) planes[tid * words + (M >> 5)] = 0;   // halo word
+            const uint32_t my_groups = warp < n_sw ? summary[warp] : 0u;
+            {
+              uint32_t cnt = 0;
+              for (uint32_t gb = my_groups; gb; gb &= gb - 1)
+                cnt += __popc(emitb[(warp * 32 + __ffs(gb) - 1) * 32 + lane]);
+              cnt = __reduce_add_sync(kFull, cnt);
+              if (lane == 0) sh.scan[warp] = cnt;
+            }
+            __syncthreads();  // B2
+            // ---- compaction step 2: ordered write
+            {
+              const uint32_t mine = sh.scan[lane];
+              uint32_t before = __reduce_add_sync(kFull, lane < warp ? mine : 0u) + sh.out_n;
+              const uint32_t all = __reduce_add_sync(kFull, mine);
+              for (uint32_t gb = my_groups; gb; gb &= gb - 1) {
+                const uint32_t g = warp * 32 + __ffs(gb) - 1;
+                uint32_t bits = emitb[g * 32 + lane];
+                emitb[g * 32 + lane] = 0;
+                const uint32_t cnt = __popc(bits);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                  const uint32_t v = __shfl_up_sync(kFull, incl, o);
+                  if (lane >= o) incl += v;
+                }
+                uint32_t slot = before + incl - cnt;
+                while (bits) {
+                  const uint32_t b = __ffs(bits) - 1;
+                  bits &= bits - 1;
+                  if (slot < out_cap) out[slot] = (base + g * 1024 + lane * 32 + b) << r;
+                  ++slot;
+                }
+                before += __shfl_sync(kFull, incl, 31);
+              }
+              if (warp < n_sw && lane == 0) summary[warp] = 0;
+              __syncthreads();  // C
+              if (tid == 0) sh.out_n += all;
+            }
+            t = tn;
+          }
+          __syncthreads();
+        }
+      }
+      __syncthreads();
+      // ---- hand the query's candidates over
+      const uint32_t n = sh.out_n;
+      if (attempt == 0) {
+        if (tid == 0) {
+          sh.base = n ? atomicAdd(p.cand_cursor, (unsigned long long)n) : 0ull;
+          if (n && sh.base + n > p.cand_capacity) atomicExch(p.overflow, 1);
+        }
+        __syncthreads();
+        const unsigned long long cbase = sh.base;
+        const bool fits = cbase + n <= p.cand_capacity;
+        if (tid == 0) {
+          p.cand_off[q] = (uint32_t)cbase;
+          p.cand_cnt[q] = fits ? n : 0u;
+        }
+        if (!fits || n == 0) break;
+        if (n <= p.staging_cap) {
+          for (uint32_t i = tid; i < n; i += kSearchThreads) p.cand_start[cbase + i] = staging[i];
+          break;
+        }
+        out = p.cand_start + cbase;   // more candidates than the staging area: redo in place
+        out_cap = n;
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && sh.visited) atomicAdd(p.positions_visited, sh.visited);
+}
+
 // Generic dynamic shared memory size for a tile of M regions.
 size_t search_smem_bytes(int T, uint32_t M) {
   const uint32_t words = M / 32 + 1;
@@ -259,20 +580,29 @@ size_t search_smem_bytes(int T, uint32_t M) {
 uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions) {
   uint32_t m = 1024u * 1024u;
   while (m > 1024 && search_smem_bytes(T, m) + sizeof(SearchShared) + 256 > smem_limit) m -= 1024;
+  while (m > 1024 && search_smem_bytes(T, m) + sizeof(FastShared) + 256 > smem_limit) m -= 1024;
   const uint32_t need = ((n_regions + 1023) / 1024) * 1024;
   return m < need ? m : (need ? need : 1024);
 }
 
-cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream) {
+cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream, bool allow_fast) {
   const int T = (int)p.threshold;
   const size_t smem = search_smem_bytes(T, p.tile_regions);
+  const bool fast = allow_fast && p.list_len <= kFastLists;
   cudaError_t err = cudaSuccess;
 #define GM_LAUNCH_SEARCH(TT)                                                                   \
   case TT:                                                                                     \
-    err = cudaFuncSetAttribute(seed_search_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               (int)smem);                                                     \
-    if (err != cudaSuccess) return err;                                                        \
-    seed_search_kernel<TT><<<grid, kSearchThreads, smem, stream>>>(p);                         \
+    if (fast) {                                                                                \
+      err = cudaFuncSetAttribute(seed_search_fast_kernel<TT>,                                  \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+      if (err != cudaSuccess) return err;                                                      \
+      seed_search_fast_kernel<TT><<<grid, kSearchThreads, smem, stream>>>(p);                  \
+    } else {                                                                                   \
+      err = cudaFuncSetAttribute(seed_search_kernel<TT>,                                       \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+      if (err != cudaSuccess) return err;                                                      \
+      seed_search_kernel<TT><<<grid, kSearchThreads, smem, stream>>>(p);                       \
+    }                                                                                          \
     break;
   switch (T) {
     GM_LAUNCH_SEARCH(1)

@@ -10,12 +10,15 @@ pytestmark = pytest.mark.gpu
 WORKLOADS = ["small", "frames6", "repeats", "long", "options"]
 
 
+@pytest.mark.parametrize("fast_search", [True, False])
 @pytest.mark.parametrize("name", WORKLOADS)
-def test_stage_parity(gpu_ctx, name):
-    """(query_id, db_start) after search and (score, db_end) after SW, per candidate chunk."""
+def test_stage_parity(gpu_ctx, name, fast_search):
+    """(query_id, db_start) after search and (score, db_end) after SW, per candidate chunk;
+    both seed-search kernels (register-window and generic)."""
     db, qchunks, kw = H.workload(name)
     opt = O.Options(**kw)
     H.setup_context(gpu_ctx, db, opt)
+    gpu_ctx.set_search_variant(fast_search)
     n_stages = 0
     for qc in qchunks:
         gpu_ctx.query_upload(qc.seqs, qc.name_breaks())
@@ -31,6 +34,7 @@ def test_stage_parity(gpu_ctx, name):
                 assert np.array_equal(ends, gends), np.flatnonzero(ends != gends)[:10]
                 n_stages += 1
     assert n_stages > 0
+    gpu_ctx.set_search_variant(True)
 
 
 @pytest.mark.parametrize("deferred", [True, False])
