@@ -24,7 +24,8 @@ EXTENDED_SYMBOLS = ["gm_version", "gm_last_error", "gm_device_count", "gm_create
                     "gm_search", "gm_chunk_rule", "gm_candidates_download", "gm_score", "gm_merge",
                     "gm_db_build_index", "gm_db_download_index", "gm_results_clear",
                     "gm_results_device", "gm_stream", "gm_measure_dpx_peak",
-                    "gm_set_deferred_traceback", "gm_traceback_pending", "gm_set_search_variant"]
+                    "gm_set_deferred_traceback", "gm_traceback_pending", "gm_set_search_variant",
+                    "gm_align_prepare", "gm_align_merge"]
 
 HIT_DTYPE = np.dtype([("query_id", "<u4"), ("db_id", "<u4"), ("db_chunk", "<u4"), ("score", "<u4"),
                       ("db_start", "<u4"), ("db_end", "<u4"), ("aln_len", "<u4"),
@@ -79,6 +80,8 @@ def load():
     L.gm_db_release.argtypes = [vp, C.c_uint32]
     L.gm_query_upload.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
     L.gm_align_chunk.argtypes = [vp, C.c_uint32, C.POINTER(GmStats)]
+    L.gm_align_prepare.argtypes = [vp, C.c_uint32, C.POINTER(GmStats)]
+    L.gm_align_merge.argtypes = [vp, C.POINTER(GmStats)]
     L.gm_results_download.argtypes = [vp, vp, vp]
     L.gm_results_upload.argtypes = [vp, vp, vp]
     L.gm_search.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_uint64), C.POINTER(GmStats)]
@@ -230,6 +233,13 @@ class Context:
     def align_chunk(self, chunk_id: int, stats: Optional[GmStats] = None):
         self._check(self.L.gm_align_chunk(self.h, chunk_id,
                                           C.byref(stats) if stats is not None else None))
+
+    def align_prepare(self, chunk_id: int, stats: Optional[GmStats] = None):
+        self._check(self.L.gm_align_prepare(self.h, chunk_id,
+                                            C.byref(stats) if stats is not None else None))
+
+    def align_merge(self, stats: Optional[GmStats] = None):
+        self._check(self.L.gm_align_merge(self.h, C.byref(stats) if stats is not None else None))
 
     def results(self):
         hits = np.zeros((self.n_queries, self.cap), dtype=HIT_DTYPE)

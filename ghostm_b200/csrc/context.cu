@@ -835,7 +835,7 @@ extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *s
   return 0;
 }
 
-extern "C" int gm_align_chunk(gm_context *c, uint32_t id, gm_stats *stats) {
+extern "C" int gm_align_prepare(gm_context *c, uint32_t id, gm_stats *stats) {
   uint64_t total = 0;
   if (int r = gm_search(c, id, nullptr, &total, stats)) return r;
   uint32_t first = 0;
@@ -846,11 +846,32 @@ extern "C" int gm_align_chunk(gm_context *c, uint32_t id, gm_stats *stats) {
                                        c->opt.max_list_length, &n, &last);
     if (n == 0) break;  // aligner.cpp:136-139
     if (int r = gm_score(c, first, end, nullptr, nullptr, stats)) return r;
+    if (last) break;
+    first = end;
+  }
+  return 0;
+}
+
+extern "C" int gm_align_merge(gm_context *c, gm_stats *stats) {
+  if (int r = check_ctx(c)) return r;
+  if (c->cur_chunk < 0) return fail(GM_ERR_ARGUMENT, "gm_align_prepare must run first");
+  uint32_t first = 0;
+  while (true) {
+    uint64_t n = 0;
+    int last = 0;
+    const uint32_t end = gm_chunk_rule(c->h_counts.data(), c->n_queries, first,
+                                       c->opt.max_list_length, &n, &last);
+    if (n == 0) break;
     if (int r = gm_merge(c, first, end, stats)) return r;
     if (last) break;
     first = end;
   }
   return 0;
+}
+
+extern "C" int gm_align_chunk(gm_context *c, uint32_t id, gm_stats *stats) {
+  if (int r = gm_align_prepare(c, id, stats)) return r;
+  return gm_align_merge(c, stats);
 }
 
 extern "C" int gm_results_download(gm_context *c, gm_hit *hits, uint32_t *counts) {
@@ -894,6 +915,7 @@ extern "C" int gm_results_device(gm_context *c, void **hits, void **counts) {
   if (int r = ensure_query_state(c)) return r;
   if (hits) *hits = c->hits[c->cur_hits].p;
   if (counts) *counts = c->hit_cnt[c->cur_hits].p;
+  c->pending = true;  // the caller may overwrite the lists (peer-to-peer receive)
   return 0;
 }
 

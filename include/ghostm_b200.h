@@ -166,6 +166,12 @@ int gm_query_upload(gm_context *ctx, const uint8_t *seqs, uint32_t n_queries, ui
  * Chunks must be presented in ascending db order (Merge carries state, aligner.cpp:114-174). */
 int gm_align_chunk(gm_context *ctx, uint32_t chunk_id, gm_stats *stats);
 
+/* gm_align_chunk in two halves, for pipelines that receive the carried hit lists from another
+ * GPU while this one is already searching: prepare = seed search + SW extension of every
+ * candidate chunk (independent of the hit lists), merge = the Merge (+TraceBack) calls. */
+int gm_align_prepare(gm_context *ctx, uint32_t chunk_id, gm_stats *stats);
+int gm_align_merge(gm_context *ctx, gm_stats *stats);
+
 /* Hit lists of the resident query chunk: hits[n_queries][cap] with cap = max(best,1),
  * counts[n_queries].  Lists live at the last query of each same-name run (aligner.cpp:701). */
 int gm_results_download(gm_context *ctx, gm_hit *hits, uint32_t *counts);

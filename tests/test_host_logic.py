@@ -1,0 +1,191 @@
+"""CPU: formats, the C ABI surface, the chunk rule, the introsort restatement, the gloo ring."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from ghostm_b200 import capi, formats, ring, synth
+from oracle import oracle as O
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """include/ghostm_b200.h is the contract: every function it declares must be exported."""
+    header = open(os.path.join(ROOT, "include", "ghostm_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", header))
+    names -= {"defined"}
+    assert {"InitGpu", "SearchNextGpu", "CalculateScoreGpu", "gm_align_chunk"} <= names
+    assert names == set(capi.LEGACY_SYMBOLS) | set(capi.EXTENDED_SYMBOLS)
+    lib = ctypes.CDLL(capi.LIB_PATH)      # loads without a GPU; no compute call is made here
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+    assert b"sm_100a" in capi.load().gm_version()
+
+
+def test_product_does_not_touch_the_oracle():
+    """The oracle is test infrastructure: nothing under ghostm_b200/ may import or link it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ghostm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("the oracle", "").replace("oracle)", ""), (dirpath, f)
+
+
+@pytest.mark.parametrize("max_list", [0, 1, 7, 50, 10**9])
+def test_chunk_rule_matches_search_next(max_list):
+    """gm_chunk_rule (host side of the C ABI) against SearchNextCpu's carry logic restated in the
+    oracle, on the candidate counts of a real search (aligner.cpp:383-389, 511-519)."""
+    db, qchunks, _ = H.workload("repeats")
+    qc, chunk = qchunks[0], db.chunks[0]
+    opt = O.Options(max_list_length=max_list)
+    counts = np.array([O.search_query(qc.seqs[i], chunk, opt).shape[0] for i in range(qc.n)],
+                      dtype=np.uint32)
+    ref = [(ids.min(), ids.max() + 1, ids.shape[0]) for ids, _ in O.search_chunks(qc.seqs, chunk, opt)]
+    got, first = [], 0
+    while True:
+        end, n, last = capi.chunk_rule(counts, first, max_list)
+        if n == 0:
+            break
+        nz = [q for q in range(first, end) if counts[q]]
+        got.append((nz[0], nz[-1] + 1, n))
+        if last:
+            break
+        first = end
+    assert got == ref
+
+
+def test_introsort_restatement_matches_libstdcxx(tmp_path):
+    """gmo_std_sort_hits (C restatement) vs the real std::sort of this toolchain, tie-heavy input."""
+    src = tmp_path / "s.cpp"
+    src.write_text("""
+#include <algorithm>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+struct R { uint32_t score, idx; };
+int main() { uint32_t n; std::vector<R> v;
+  while (fread(&n, 4, 1, stdin) == 1) { v.resize(n); if (n) fread(v.data(), 8, n, stdin);
+    std::sort(v.begin(), v.end(), [](const R &a, const R &b) { return a.score > b.score; });
+    for (auto &r : v) fwrite(&r.idx, 4, 1, stdout); }
+  return 0; }
+""")
+    exe = tmp_path / "s"
+    subprocess.check_call(["g++", "-O2", "-o", str(exe), str(src)])
+    rng = np.random.default_rng(5)
+    cases = [rng.integers(20, 20 + k, size=n).astype(np.uint32)
+             for n in (0, 1, 2, 15, 16, 17, 33, 100, 700, 5000) for k in (1, 3, 40)]
+    cases.append(np.arange(3000, dtype=np.uint32))            # sorted ascending: worst pivots
+    cases.append(np.tile(np.array([5, 9], dtype=np.uint32), 800))
+    inp = b""
+    for c in cases:
+        rec = np.stack([c, np.arange(c.shape[0], dtype=np.uint32)], axis=1)
+        inp += np.uint32(c.shape[0]).tobytes() + rec.tobytes()
+    out = np.frombuffer(subprocess.run([str(exe)], input=inp, stdout=subprocess.PIPE, check=True).stdout,
+                        dtype=np.uint32)
+    off = 0
+    for c in cases:
+        hits = np.zeros(c.shape[0], dtype=O.HIT_DTYPE)
+        hits["score"] = c
+        hits["query_id"] = np.arange(c.shape[0])
+        O.lib().gmo_std_sort_hits(hits.ctypes.data, c.shape[0])
+        assert np.array_equal(hits["query_id"], out[off:off + c.shape[0]])
+        off += c.shape[0]
+
+
+@pytest.mark.skipif(O.ref_bin() is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_writers_byte_identical_to_reference(tmp_path):
+    dbs, dbn = synth.protein_db(81, 1_200_000)
+    dbs[3][5:9] = formats.BASE_X          # X inside k-mers, a sequence as short as the seed
+    dbs.insert(7, dbs[7][:4].copy())
+    dbn.insert(7, "tiny")
+    qs, qn = synth.queries_from_db(82, dbs, 90, 75, min_length=10)
+    formats.write_fasta(str(tmp_path / "db.fa"), dbn, dbs, 70)
+    formats.write_fasta(str(tmp_path / "q.fa"), qn, qs)
+    for cmd in (["db", "-i", str(tmp_path / "db.fa"), "-o", str(tmp_path / "rdb"), "-l", "1"],
+                ["qry", "-i", str(tmp_path / "q.fa"), "-o", str(tmp_path / "rq"), "-l", "60"]):
+        subprocess.check_call([O.ref_bin()] + cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    formats.write_db(str(tmp_path / "mdb"), formats.make_db(dbs, dbn, 4, 1))
+    formats.write_queries(str(tmp_path / "mq"), formats.make_query_chunks(qs, qn, 60, 128))
+    n = 0
+    for f in sorted(os.listdir(tmp_path)):
+        if f.startswith(("rdb", "rq")):
+            assert (tmp_path / f).read_bytes() == (tmp_path / ("m" + f[1:])).read_bytes(), f
+            n += 1
+    assert n >= 12
+    db = formats.read_db(str(tmp_path / "rdb"))
+    for ch in db.chunks:   # the oracle's index restatement too
+        kc = np.zeros_like(ch.keys_count)
+        pos = np.zeros(ch.seq.shape[0], dtype=np.uint32)
+        k = O.lib().gmo_build_index(ch.seq, ch.seq.shape[0], ch.seq_starts, ch.n_seqs, ch.seed, kc, pos)
+        assert k == ch.positions.shape[0]
+        assert np.array_equal(kc, ch.keys_count) and np.array_equal(pos[:k], ch.positions)
+
+
+def test_chunks_of_rank_partition():
+    for n in (1, 3, 8, 9):
+        for w in (1, 2, 4, 8):
+            parts = [ring.chunks_of_rank(n, r, w) for r in range(w)]
+            assert sum(parts, []) == list(range(n))
+
+
+_RING_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from ghostm_b200 import ring
+from oracle import oracle as O
+from tests import helpers as H
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+db, qchunks, kw = H.workload("small")
+opt = O.Options(**kw)
+qc = qchunks[0]
+
+class OracleEngine(ring.Engine):
+    def __init__(self):
+        self.res = O.ResultLists(qc.n, opt.best)
+        self.t_hits = torch.from_numpy(self.res.hits.view(np.int32).reshape(-1))
+        self.t_counts = torch.from_numpy(self.res.counts.view(np.int32))
+        self.stage = None
+    def prepare(self, c):
+        ch = db.chunks[c]
+        self.stage = (c, [(ids, st) + O.calculate_score(qc.seqs, ch, ids, st, opt)
+                          for ids, st in O.search_chunks(qc.seqs, ch, opt)])
+    def merge(self):
+        c, parts = self.stage
+        for ids, st, sc, en in parts:
+            O.merge(self.res, qc, db.chunks[c], c, ids, st, sc, en, opt)
+    def list_tensors(self):
+        return self.t_hits, self.t_counts
+
+eng = OracleEngine()
+final = ring.ring_step(eng, dist, rank, world, ring.chunks_of_rank(len(db.chunks), rank, world))
+if final:
+    single = O.align_chunk(qc, db, opt)
+    assert np.array_equal(single.counts, eng.res.counts)
+    for i in range(qc.n):
+        assert single.hits[i, :single.counts[i]].tobytes() == eng.res.hits[i, :single.counts[i]].tobytes()
+    print("RING_OK", int(single.counts.sum()))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_ring_over_gloo_world2(tmp_path):
+    """db chunks sharded over 2 ranks, hit lists handed rank 0 -> rank 1 (gloo): the last rank must
+    hold exactly the single-process result."""
+    script = tmp_path / "w.py"
+    script.write_text(_RING_WORKER.format(root=ROOT))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29611",
+                          str(script)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "RING_OK" in out.stdout
