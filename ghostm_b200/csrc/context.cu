@@ -25,7 +25,8 @@ size_t merge_smem_bytes(uint32_t elems_per_warp);
 cudaError_t merge_launch(const MergeParams &p, int sm_count, cudaStream_t stream);
 int traceback_grid(int sm_count);
 int traceback_threads();
-cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_t stream);
+cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_t stream, bool fast);
+bool traceback_fast_ok(uint32_t query_len, int open_gap, int extend_gap);
 cudaError_t collect_pending_launch(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
                                    uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
                                    uint32_t *n_jobs, int sm_count, cudaStream_t stream);
@@ -224,7 +225,8 @@ struct gm_context {
   DevBuf<int> tb_work;
   DevBuf<ChunkRef> chunk_tab;
   bool chunk_tab_dirty = true;
-  bool search_fast = true;   // register-window search kernel when the options allow it
+  bool search_fast = true;   // balanced register-resident search kernel when the options allow it
+  bool traceback_fast = true;
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits
   uint32_t serial = 0;
@@ -712,10 +714,15 @@ int run_traceback(gm_context *c, gm_hit *hits) {
   t.open_gap = c->opt.open_gap;
   t.extend_gap = c->opt.extend_gap;
   t.base_len = c->query_len + 2 * c->opt.extend * 2 * (1u << c->opt.log_region);  // aligner.cpp:775
-  const size_t tb_threads = (size_t)traceback_grid(c->sm_count) * traceback_threads();
-  GM_CUDA(c->tb_work.ensure(tb_threads * 4 * (c->query_len + 1)));
+  // the score range check of the packed SW kernel also covers the 16-bit H of this one
+  const bool fast = c->traceback_fast && !c->use_s32 &&
+                    traceback_fast_ok(c->query_len, c->opt.open_gap, c->opt.extend_gap);
+  if (!fast) {
+    const size_t tb_threads = (size_t)traceback_grid(c->sm_count) * traceback_threads();
+    GM_CUDA(c->tb_work.ensure(tb_threads * 4 * (c->query_len + 1)));
+  }
   t.work = c->tb_work.p;
-  GM_CUDA(traceback_launch(t, c->sm_count, c->stream));
+  GM_CUDA(traceback_launch(t, c->sm_count, c->stream, fast));
   return 0;
 }
 
@@ -724,6 +731,7 @@ int run_traceback(gm_context *c, gm_hit *hits) {
 extern "C" int gm_set_search_variant(gm_context *c, int fast) {
   if (int r = check_ctx(c)) return r;
   c->search_fast = fast != 0;
+  c->traceback_fast = fast != 0;
   return 0;
 }
 

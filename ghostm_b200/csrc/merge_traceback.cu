@@ -125,24 +125,42 @@ __device__ void insertion_sort_(Rec *first, Rec *last) {
   }
 }
 
+// std::sort(first, first + n, comp), replayed LAZILY.  Only a prefix of the sorted array is ever
+// read by the Merge walk (it stops after `best` accepted hits), and the prefix can be produced
+// without touching most of the array, move for move identical to the full sort:
+//  * __introsort_loop recurses into [cut, last) and loops on [first, cut); the two halves are
+//    disjoint and never exchange elements afterwards, so the right halves can wait on a stack
+//    until the walk actually needs positions inside them;
+//  * after the loop phase the array is a sequence of blocks of <= 16 elements (or heap-sorted
+//    ranges), each block >= the next one under the comparator; __final_insertion_sort inserts
+//    elements left to right and an element never crosses into an earlier block (the comparison
+//    is strict), so positions [0, e) are final as soon as every element before the block
+//    boundary e has been inserted.
 template <typename Rec>
-__device__ void std_sort_replay(Rec *first, long n) {
-  if (n <= 0) return;
-  Rec *last = first + n;
-  // __introsort_loop with an explicit stack for the (cut, last) halves
-  struct Frame { Rec *first, *last; int depth; };
+struct LazySort {
+  struct Frame { long first, last; int depth; };
+  Rec *a;
+  long n;
+  long looped;     // [0, looped) went through the introsort loop phase (block boundary)
+  long final_end;  // [0, final_end) is in its final sorted place
+  int sp;
   Frame stack[64];
-  int sp = 0;
-  int lg = 0;
-  for (long m = n; m > 1; m >>= 1) ++lg;
-  stack[sp++] = Frame{first, last, lg * 2};
-  while (sp > 0) {
+
+  __device__ void init(Rec *arr, long count) {
+    a = arr;
+    n = count;
+    looped = 0;
+    final_end = 0;
+    sp = 0;
+    int lg = 0;
+    for (long m = count; m > 1; m >>= 1) ++lg;
+    if (count > 0) stack[sp++] = Frame{0, count, lg * 2};
+  }
+
+  __device__ void loop_next_block() {  // __introsort_loop on the leftmost pending range
     Frame fr = stack[--sp];
-    Rec *f = fr.first, *l = fr.last;
+    Rec *f = a + fr.first, *l = a + fr.last;
     int depth = fr.depth;
-    // The reference recursion handles [cut, last) first, then loops on [first, cut).  The two
-    // halves are disjoint and each is processed independently of the other, so any order of
-    // handling gives the same final array; an explicit stack keeps it iterative.
     while (l - f > 16) {
       if (depth == 0) {
         heap_sort_(f, l);
@@ -150,14 +168,14 @@ __device__ void std_sort_replay(Rec *first, long n) {
       }
       --depth;
       Rec *mid = f + (l - f) / 2;
-      Rec *a = f + 1, *b = mid, *c = l - 1;  // __move_median_to_first(f, a, b, c)
-      if (comp(*a, *b)) {
-        if (comp(*b, *c)) swap_(f, b);
-        else if (comp(*a, *c)) swap_(f, c);
-        else swap_(f, a);
-      } else if (comp(*a, *c)) swap_(f, a);
-      else if (comp(*b, *c)) swap_(f, c);
-      else swap_(f, b);
+      Rec *x = f + 1, *y = mid, *z = l - 1;    // __move_median_to_first(f, x, y, z)
+      if (comp(*x, *y)) {
+        if (comp(*y, *z)) swap_(f, y);
+        else if (comp(*x, *z)) swap_(f, z);
+        else swap_(f, x);
+      } else if (comp(*x, *z)) swap_(f, x);
+      else if (comp(*y, *z)) swap_(f, z);
+      else swap_(f, y);
       Rec *lo = f + 1, *hi = l;                // __unguarded_partition(f + 1, l, f)
       const Rec pivot = *f;
       while (true) {
@@ -168,18 +186,33 @@ __device__ void std_sort_replay(Rec *first, long n) {
         swap_(lo, hi);
         ++lo;
       }
-      Rec *cut = lo;
-      stack[sp++] = Frame{cut, l, depth};
-      l = cut;
+      stack[sp++] = Frame{(long)(lo - a), (long)(l - a), depth};
+      l = lo;
     }
+    looped = l - a;
   }
-  if (n > 16) {  // __final_insertion_sort
-    insertion_sort_(first, first + 16);
-    for (Rec *i = first + 16; i != last; ++i) unguarded_linear_insert_(i);
-  } else {
-    insertion_sort_(first, last);
+
+  // make position i final; returns false if i >= n
+  __device__ bool ensure(long i) {
+    if (i >= n) return false;
+    while (final_end <= i) {
+      if (looped == final_end) loop_next_block();
+      for (long k = final_end; k < looped; ++k) {   // __final_insertion_sort, element k
+        if (k == 0) continue;
+        Rec *e = a + k;
+        if ((n <= 16 || k < 16) && comp(*e, *a)) {  // __insertion_sort's guarded branch
+          const Rec val = *e;
+          for (Rec *q = e; q != a; --q) *q = *(q - 1);
+          *a = val;
+        } else {
+          unguarded_linear_insert_(e);
+        }
+      }
+      final_end = looped;
+    }
+    return true;
   }
-}
+};
 
 // DB::GetID, db.h:94-120
 __device__ uint32_t db_get_id(const uint32_t *pos, uint32_t n_seqs, uint32_t seq_len, uint32_t position) {
@@ -223,11 +256,13 @@ __device__ void merge_run(const MergeParams &p, Rec *list, uint32_t n_new, uint3
   }
   __syncwarp();
   if (lane == 0) {
-    std_sort_replay(list, (long)n);
-    // ---- walk (aligner.cpp:703-725 / :746-768)
+    LazySort<Rec> sorter;
+    sorter.init(list, (long)n);
+    // ---- walk (aligner.cpp:703-725 / :746-768) over the lazily sorted list
     uint32_t out = 0;
     gm_hit *dst = p.new_hits + (size_t)ql * p.cap;
     for (uint32_t it = 0; it < n; ++it) {
+      sorter.ensure((long)it);
       const Rec r = list[it];
       const uint32_t ref = kWide ? (uint32_t)r : ((uint32_t)r & 0xFFFFu);
       const bool carried = kWide ? (ref & 0x80000000u) != 0 : (ref & kCarriedFlag) != 0;
@@ -390,6 +425,76 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TracebackParams p)
 #undef GM_COL
 }
 
+// Register-resident TraceBack for L <= R rows: one thread per hit, the column state of row k is
+// two packed words, (H << 16 | E) and (matches << 16 | alignment length), so the reverse DP of a
+// hit never leaves the register file; the score matrix (16-bit) and the thread's own query
+// residues (transposed, one byte column per thread) sit in shared memory.
+template <int R>
+__global__ void __launch_bounds__(128, 2) traceback_reg_kernel(const TracebackParams p) {
+  __shared__ int16_t mat[kAlphabet * kAlphabet];
+  __shared__ uint8_t qs[R][128];
+  for (int i = threadIdx.x; i < kAlphabet * kAlphabet; i += blockDim.x) mat[i] = (int16_t)p.matrix[i];
+  __syncthreads();
+  const uint32_t n_jobs = *p.n_jobs;
+  const int L = (int)p.query_len;
+  const int go = p.open_gap, ge = p.extend_gap;
+  for (uint32_t job = blockIdx.x * blockDim.x + threadIdx.x; job < n_jobs;
+       job += gridDim.x * blockDim.x) {
+    gm_hit h = p.hits[p.jobs[job]];
+    const ChunkRef chunk = p.chunks[h.db_chunk];
+    const uint8_t *query = p.queries + (size_t)h.query_id * L;
+#pragma unroll 5
+    for (int k = 0; k < R; ++k) qs[k][threadIdx.x] = k < L ? query[k] : (uint8_t)kBaseX;
+    const uint32_t db_offset = h.db_end;
+    uint32_t len = p.base_len;
+    if (db_offset < len) len = db_offset + 1;                         // aligner.cpp:802-805
+    uint32_t he[R], pay[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) { he[k] = 0; pay[k] = 0; }
+    int max_score = 0;
+    uint32_t max_start = 0, max_pay = 0;
+    for (uint32_t j = 0; j < len; ++j) {
+      const uint32_t c = chunk.seq[db_offset - j];
+      if (c == kSeqEnd) break;                                        // aligner.cpp:927-929
+      const int16_t *row = mat + c * kAlphabet;
+      int temp_score = 0, del = 0, below_h = 0;
+      uint32_t temp_pay = 0, below_pay = 0;
+#pragma unroll
+      for (int k = R - 1; k >= 0; --k) {
+        if (k < L) {
+          const uint32_t old = he[k], old_pay = pay[k];
+          const int old_h = (int)old >> 16;
+          int ins = (int)(int16_t)(old & 0xFFFFu);
+          const uint32_t qk = qs[k][threadIdx.x];
+          const int s = temp_score + row[qk];
+          int local = 0;
+          uint32_t np = 0;
+          if (s > 0) { local = s; np = temp_pay + (c == qk ? 0x10001u : 0x1u); }
+          ins = max(ins + ge, old_h + go);
+          if (ins > local) { local = ins; np = old_pay + 1; }
+          del = max(del + ge, below_h + go);
+          if (del > local) { local = del; np = below_pay + 1; }
+          temp_score = old_h;
+          temp_pay = old_pay;
+          he[k] = ((uint32_t)local << 16) | ((uint32_t)ins & 0xFFFFu);
+          pay[k] = np;
+          below_h = local;
+          below_pay = np;
+          if (local > max_score) { max_score = local; max_start = j; max_pay = np; }  // first max
+        }
+      }
+    }
+    const uint32_t seq_pos = chunk.seq_starts[h.db_id];
+    const uint32_t max_match = max_pay >> 16, max_len = max_pay & 0xFFFFu;
+    h.db_start = db_offset - max_start - seq_pos;                     // aligner.cpp:941, :715
+    h.db_end = db_offset - seq_pos;                                   // :716
+    h.seq_id = (float)max_match / (float)(int)max_len;                // :945
+    h.aln_len = max_len;
+    h.aln_match = max_match;
+    p.hits[p.jobs[job]] = h;
+  }
+}
+
 // Collect the result slots whose TraceBack is pending and whose db chunk is resident here.
 __global__ void collect_pending_kernel(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
                                        uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
@@ -428,7 +533,20 @@ cudaError_t merge_launch(const MergeParams &p, int sm_count, cudaStream_t stream
 int traceback_grid(int sm_count) { return sm_count * 8; }
 int traceback_threads() { return 128; }
 
-cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_t stream) {
+// True when the register-resident kernel covers this query length and gap/score range.
+bool traceback_fast_ok(uint32_t query_len, int open_gap, int extend_gap) {
+  return query_len <= 80 && open_gap > -8000 && extend_gap > -8000 && open_gap <= 0 && extend_gap <= 0;
+}
+
+cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_t stream, bool fast) {
+  if (fast && traceback_fast_ok(p.query_len, p.open_gap, p.extend_gap)) {
+    const int grid = sm_count * 2;
+    if (p.query_len <= 32) traceback_reg_kernel<32><<<grid, 128, 0, stream>>>(p);
+    else if (p.query_len <= 64) traceback_reg_kernel<64><<<grid, 128, 0, stream>>>(p);
+    else if (p.query_len <= 75) traceback_reg_kernel<75><<<grid, 128, 0, stream>>>(p);
+    else traceback_reg_kernel<80><<<grid, 128, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
   traceback_kernel<<<traceback_grid(sm_count), traceback_threads(), 0, stream>>>(p);
   return cudaGetLastError();
 }

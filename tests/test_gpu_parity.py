@@ -37,15 +37,16 @@ def test_stage_parity(gpu_ctx, name, fast_search):
     gpu_ctx.set_search_variant(True)
 
 
-@pytest.mark.parametrize("deferred", [True, False])
+@pytest.mark.parametrize("deferred,fast", [(True, True), (False, True), (False, False)])
 @pytest.mark.parametrize("name", WORKLOADS)
-def test_hit_lists(gpu_ctx, name, deferred):
+def test_hit_lists(gpu_ctx, name, deferred, fast):
     """Final hit lists (Merge + TraceBack on the device), with TraceBack deferred to the
     survivors (default) and in the reference order (inside every Merge)."""
     db, qchunks, kw = H.workload(name)
     opt = O.Options(**kw)
     H.setup_context(gpu_ctx, db, opt)
     gpu_ctx.set_deferred_traceback(deferred)
+    gpu_ctx.set_search_variant(fast)     # fast = register-resident search / TraceBack kernels
     for qc in qchunks:
         ref = O.align_chunk(qc, db, opt)
         gpu_ctx.query_upload(qc.seqs, qc.name_breaks())
@@ -58,3 +59,4 @@ def test_hit_lists(gpu_ctx, name, deferred):
             assert ok, (name, i, field, hits[i, :counts[i]], ref.hits[i, :counts[i]])
     assert int(ref.counts.sum()) > 0
     gpu_ctx.set_deferred_traceback(True)
+    gpu_ctx.set_search_variant(True)
