@@ -50,8 +50,8 @@ def parse_args():
     ap.add_argument("--db-residues", type=float, default=1e9)
     ap.add_argument("--chunk-mib", type=float, default=120.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-mib", type=float, default=8.0)
-    ap.add_argument("--cpu-sample-queries", type=int, default=256)
+    ap.add_argument("--cpu-sample-mib", type=float, default=32.0)
+    ap.add_argument("--cpu-sample-queries", type=int, default=2048)
     return ap.parse_args()
 
 
@@ -207,7 +207,7 @@ def run_ours(a):
             ctx.query_upload_ptr(q_pinned[b].data_ptr(), a.queries, a.length)
         else:
             ctx.results_clear()
-        final = ring.ring_step(engine, dist, rank, world, mine)
+        final = ring.ring_step(engine, dist, rank, world, n_chunks)
         if world == 1:
             ctx.traceback_pending(stats)
         if e2e and final:

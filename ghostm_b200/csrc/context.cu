@@ -17,7 +17,8 @@ namespace gm {
 int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips);
 cudaError_t sw_extend_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream);
 cudaError_t sw_extend_s32_launch(const SwParams &p, int sm_count, cudaStream_t stream);
-uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions);
+uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions, bool fast);
+bool search_uses_fast(uint32_t list_len, bool allow_fast);
 cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream, bool allow_fast);
 int search_max_list_len();
 int search_max_threshold();
@@ -467,7 +468,7 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
   DbChunk &ch = c->chunks[id];
   GM_CUDA(c->cand_start.ensure(c->cand_capacity));
   const int grid = c->sm_count;
-  GM_CUDA(c->staging.ensure((size_t)grid * c->staging_cap));
+  GM_CUDA(c->staging.ensure((size_t)grid * 2 * c->staging_cap));  // the fast kernel runs 2 CTAs per SM
   GM_CUDA(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
   GM_CUDA(cudaMemsetAsync(c->small.p, 0, 8 * sizeof(uint32_t), c->stream));
   c->cur_chunk = -1;
@@ -492,7 +493,8 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     p.threshold = c->opt.threshold;
     p.list_len = c->list_len;
     p.n_regions = (ch.seq_len >> c->opt.log_region) + 1;
-    p.tile_regions = search_tile_regions((int)p.threshold, c->smem_optin, p.n_regions);
+    const bool fast = search_uses_fast(p.list_len, c->search_fast);
+    p.tile_regions = search_tile_regions((int)p.threshold, c->smem_optin, p.n_regions, fast);
     p.cand_off = c->cand_off.p;
     p.cand_cnt = c->cand_cnt.p;
     p.cand_start = c->cand_start.p;
@@ -1176,6 +1178,10 @@ extern "C" uint32_t SearchNextGpu(uint32_t query_sequence_length, uint32_t numbe
   const uint32_t end = gm_chunk_rule(g_legacy_counts.data(), number_query_sequences, start_query_id,
                                      max_number_alignments, &n, &last);
   if (n == 0) return 0;
+  if (n > max_number_alignments) {  // one query alone exceeds the caller's starts[] buffer
+    g_error = "SearchNextGpu: a single query has more candidates than max_number_alignments";
+    legacy_die("SearchNextGpu");
+  }
   g_legacy_first = start_query_id;
   g_legacy_end = end;
   uint32_t cum = 0;

@@ -1,0 +1,439 @@
+// ghostm_b200 - host driver: `ghostm_b200 aln ...`, a drop-in for the reference's `ghostm aln`.
+//
+// Same command line (reference aligner.cpp:225-345), same db / query file formats (db_reader.cpp,
+// db.cpp, query_reader.cpp, query.cpp), same tab-separated hit list (aligner.cpp:951-1012).  The
+// search itself - seed lookup, candidate chunking, SW extension, Merge, TraceBack - runs on the
+// GPU through the C ABI of include/ghostm_b200.h; nothing here computes an alignment and there is
+// no CPU fallback.  `-D` takes one device id like the reference, or a comma separated list: the
+// db chunks are then spread round-robin over the devices and the per-query hit lists are handed
+// from device to device in db order through host memory, which keeps the result identical to a
+// single-device (and to the reference's) run.
+#include <getopt.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <condition_variable>
+#include <fstream>
+#include <iostream>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/ghostm_b200.h"
+
+namespace {
+
+constexpr int kAlphabet = 32;      // common.h:31
+constexpr uint8_t kBaseX = 23;     // common.h:35
+
+// ---- residue codes (sequence.cpp:63-87): A0 R1 N2 D3 C4 Q5 E6 G7 H8 I9 L10 K11 M12 F13 P14 S15
+// T16 W17 Y18 V19 B20 J21 Z22 X23 *24; everything else is X.
+int residue_code(char ch) {
+  static const char *letters = "ARNDCQEGHILKMFPSTWYVBJZX*";
+  if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 'a' + 'A');
+  const char *p = ch ? strchr(letters, ch) : nullptr;
+  return p ? (int)(p - letters) : kBaseX;
+}
+
+// ---- score matrix (score_matrix_reader.cpp:44-113) -------------------------------------------
+const char *kBlosum62 =
+    "   A  R  N  D  C  Q  E  G  H  I  L  K  M  F  P  S  T  W  Y  V  B  Z  X  *\n"
+    "A  4 -1 -2 -2  0 -1 -1  0 -2 -1 -1 -1 -1 -2 -1  1  0 -3 -2  0 -2 -1  0 -4\n"
+    "R -1  5  0 -2 -3  1  0 -2  0 -3 -2  2 -1 -3 -2 -1 -1 -3 -2 -3 -1  0 -1 -4\n"
+    "N -2  0  6  1 -3  0  0  0  1 -3 -3  0 -2 -3 -2  1  0 -4 -2 -3  3  0 -1 -4\n"
+    "D -2 -2  1  6 -3  0  2 -1 -1 -3 -4 -1 -3 -3 -1  0 -1 -4 -3 -3  4  1 -1 -4\n"
+    "C  0 -3 -3 -3  9 -3 -4 -3 -3 -1 -1 -3 -1 -2 -3 -1 -1 -2 -2 -1 -3 -3 -2 -4\n"
+    "Q -1  1  0  0 -3  5  2 -2  0 -3 -2  1  0 -3 -1  0 -1 -2 -1 -2  0  3 -1 -4\n"
+    "E -1  0  0  2 -4  2  5 -2  0 -3 -3  1 -2 -3 -1  0 -1 -3 -2 -2  1  4 -1 -4\n"
+    "G  0 -2  0 -1 -3 -2 -2  6 -2 -4 -4 -2 -3 -3 -2  0 -2 -2 -3 -3 -1 -2 -1 -4\n"
+    "H -2  0  1 -1 -3  0  0 -2  8 -3 -3 -1 -2 -1 -2 -1 -2 -2  2 -3  0  0 -1 -4\n"
+    "I -1 -3 -3 -3 -1 -3 -3 -4 -3  4  2 -3  1  0 -3 -2 -1 -3 -1  3 -3 -3 -1 -4\n"
+    "L -1 -2 -3 -4 -1 -2 -3 -4 -3  2  4 -2  2  0 -3 -2 -1 -2 -1  1 -4 -3 -1 -4\n"
+    "K -1  2  0 -1 -3  1  1 -2 -1 -3 -2  5 -1 -3 -1  0 -1 -3 -2 -2  0  1 -1 -4\n"
+    "M -1 -1 -2 -3 -1  0 -2 -3 -2  1  2 -1  5  0 -2 -1 -1 -1 -1  1 -3 -1 -1 -4\n"
+    "F -2 -3 -3 -3 -2 -3 -3 -3 -1  0  0 -3  0  6 -4 -2 -2  1  3 -1 -3 -3 -1 -4\n"
+    "P -1 -2 -2 -1 -3 -1 -1 -2 -2 -3 -3 -1 -2 -4  7 -1 -1 -4 -3 -2 -2 -1 -2 -4\n"
+    "S  1 -1  1  0 -1  0  0  0 -1 -2 -2  0 -1 -2 -1  4  1 -3 -2 -2  0  0  0 -4\n"
+    "T  0 -1  0 -1 -1 -1 -1 -2 -2 -1 -1 -1 -1 -2 -1  1  5 -2 -2  0 -1 -1  0 -4\n"
+    "W -3 -3 -4 -4 -2 -2 -3 -2 -2 -3 -2 -3 -1  1 -4 -3 -2 11  2 -3 -4 -3 -2 -4\n"
+    "Y -2 -2 -2 -3 -2 -1 -2 -3  2 -1 -1 -2 -1  3 -3 -2 -2  2  7 -1 -3 -2 -1 -4\n"
+    "V  0 -3 -3 -3 -1 -2 -2 -3 -3  3  1 -2  1 -1 -2 -2  0 -3 -1  4 -3 -2 -1 -4\n"
+    "B -2 -1  3  4 -3  0  1 -1  0 -3 -4  0 -3 -3 -2  0 -1 -4 -3 -3  4  1 -1 -4\n"
+    "Z -1  0  0  1 -3  3  4 -2  0 -3 -3  1 -1 -3 -1  0 -1 -3 -2 -2  1  4 -1 -4\n"
+    "X  0 -1 -1 -1 -2 -1 -1 -1 -1 -1 -1 -1 -1 -1 -2  0  0 -2 -1 -1 -1 -1 -1 -4\n"
+    "* -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4 -4  1\n";
+
+struct ScoreMatrix {
+  std::string name;
+  int32_t m[kAlphabet * kAlphabet];
+};
+
+// NCBI text format; a row/column is taken from the FIRST character of its token, at most 25
+// rows and 25 tokens per row are read, '#' lines are comments (score_matrix_reader.cpp:80-113).
+void parse_matrix(std::istream &in, ScoreMatrix *out) {
+  memset(out->m, 0, sizeof(out->m));
+  char cols[kAlphabet] = {0};
+  std::string line;
+  int line_no = 0;
+  while (std::getline(in, line)) {
+    if (line.empty() || line[0] == '#' || line_no >= 25) continue;
+    std::istringstream ss(line);
+    std::string tok;
+    char row = 0;
+    for (int i = 0; i < 25 && (ss >> tok); ++i) {
+      if (line_no == 0) cols[i] = tok[0];
+      else if (i == 0) row = tok[0];
+      else out->m[residue_code(row) * kAlphabet + residue_code(cols[i - 1])] = atoi(tok.c_str());
+    }
+    ++line_no;
+  }
+}
+
+ScoreMatrix load_matrix(const std::string &file) {
+  ScoreMatrix sm;
+  std::ifstream in(file.c_str());
+  if (in) {  // score_matrix_reader.cpp:44-60: the name is the file's basename
+    const size_t slash = file.find_last_of('/');
+    sm.name = slash == std::string::npos ? file : file.substr(slash + 1);
+    parse_matrix(in, &sm);
+  } else {   // anything that cannot be opened means the built-in BLOSUM62
+    std::istringstream def(kBlosum62);
+    sm.name = "BLOSUM62";
+    parse_matrix(def, &sm);
+  }
+  return sm;
+}
+
+// ---- statistics (statistics.cpp:40-59, 134-146) -----------------------------------------------
+struct Karlin { float lambda, K, H; };
+
+Karlin gapped_karlin(const ScoreMatrix &sm, int open_gap, int extend_gap) {
+  if (sm.name == "BLOSUM62" && open_gap == -11 && extend_gap == -1) return Karlin{0.267f, 0.041f, 0.14f};
+  if (sm.name == "PAM30" && open_gap == -9 && extend_gap == -1) return Karlin{0.294f, 0.11f, 0.61f};
+  throw std::invalid_argument("error: not support score option");
+}
+
+float bit_score(int score, const Karlin &k) {  // every operand is float (statistics.cpp:40-44)
+  return ((static_cast<float>(score) * k.lambda) - logf(k.K)) / static_cast<float>(log(2.0));
+}
+
+double e_value(int score, uint64_t search_space, const Karlin &k) {  // statistics.cpp:51-55
+  return (static_cast<float>(search_space) * k.K) * exp(static_cast<double>(-1.0 * score * k.lambda));
+}
+
+// ---- formatted files --------------------------------------------------------------------------
+template <typename T>
+bool read_vec(const std::string &path, size_t count, std::vector<T> *out, size_t skip_bytes = 0) {
+  std::ifstream in(path.c_str(), std::ios::binary);
+  if (!in) return false;
+  in.seekg((std::streamoff)skip_bytes);
+  out->resize(count);
+  in.read(reinterpret_cast<char *>(out->data()), (std::streamsize)(count * sizeof(T)));
+  return true;
+}
+
+std::vector<std::string> read_names(const std::string &path, uint32_t n) {  // db.cpp:36-61
+  std::vector<std::string> names(n);
+  std::ifstream in(path.c_str());
+  std::string line;
+  uint32_t i = 0;
+  for (; i < n && in && !in.eof(); ++i) {
+    std::getline(in, line);
+    names[i] = line;
+  }
+  if (i < n) std::cerr << "warning : couldn't read all sequence names" << std::endl;
+  return names;
+}
+
+struct DbInfo {          // <db>.inf, db_creator.cpp:243-264 / db_reader.cpp:36-50
+  int32_t division = 0;
+  uint32_t seed = 0, max_chunk_len = 0;
+  uint64_t sum_length = 0;
+};
+
+bool read_db_info(const std::string &prefix, DbInfo *info) {
+  std::ifstream in((prefix + ".inf").c_str(), std::ios::binary);
+  if (!in) return false;
+  in.read(reinterpret_cast<char *>(&info->division), 4);
+  in.read(reinterpret_cast<char *>(&info->seed), 4);
+  in.read(reinterpret_cast<char *>(&info->max_chunk_len), 4);
+  in.read(reinterpret_cast<char *>(&info->sum_length), 8);
+  return true;
+}
+
+struct DbChunk {         // <db>_<i>.{inf,seq,pos,nam,ind}
+  uint32_t n_seqs = 0, seq_len = 0, seed = 0;
+  std::vector<uint8_t> seq;
+  std::vector<uint32_t> seq_starts, keys_count, positions;
+  std::vector<std::string> names;
+};
+
+bool read_db_chunk(const std::string &prefix, int i, DbChunk *c, bool with_arrays) {
+  std::ostringstream p;
+  p << prefix << "_" << i;
+  std::vector<uint32_t> inf;
+  if (!read_vec(p.str() + ".inf", 2, &inf)) return false;
+  c->n_seqs = inf[0];
+  c->seq_len = inf[1];
+  c->names = read_names(p.str() + ".nam", c->n_seqs);
+  if (!with_arrays) return true;
+  std::vector<uint32_t> hdr;
+  if (!read_vec(p.str() + ".seq", c->seq_len, &c->seq) || !read_vec(p.str() + ".pos", c->n_seqs, &c->seq_starts) ||
+      !read_vec(p.str() + ".ind", 3, &hdr))
+    return false;
+  c->seed = hdr[0];
+  return read_vec(p.str() + ".ind", hdr[1], &c->keys_count, 12) &&
+         read_vec(p.str() + ".ind", hdr[2], &c->positions, 12 + (size_t)hdr[1] * 4);
+}
+
+struct QueryChunk {      // <q>_<i>.{inf,seq,nam}, query_creator.cpp:346-419
+  uint32_t n = 0, length = 0;
+  std::vector<uint8_t> seqs;
+  std::vector<std::string> names;
+};
+
+bool read_query_chunk(const std::string &prefix, uint32_t i, QueryChunk *q) {
+  std::ostringstream p;
+  p << prefix << "_" << i;
+  std::vector<uint32_t> inf;
+  if (!read_vec(p.str() + ".inf", 2, &inf)) return false;
+  q->n = inf[0];
+  q->length = inf[1];
+  if (!read_vec(p.str() + ".seq", (size_t)q->n * q->length, &q->seqs)) return false;
+  q->names = read_names(p.str() + ".nam", q->n);
+  return true;
+}
+
+// ---- options (aligner.cpp:225-345) ------------------------------------------------------------
+struct Options {
+  std::string output, queries, db, matrix_file = "BLOSUM62";
+  uint32_t log_region = 4, shift = 2, threshold = 2, max_list_length = 1u << 27, extend = 2, best = 10;
+  int open_gap = -11, extend_gap = -1;
+  uint32_t start_chunk = UINT32_MAX, end_chunk = UINT32_MAX;
+  int style = 0;
+  bool verbose = false;
+  std::vector<int> devices;
+};
+
+Options parse_options(int argc, char **argv) {
+  Options o;
+  int c;
+  while ((c = getopt(argc, argv, "b:d:D:e:E:G:i:l:M:o:r:s:t:S:L:y:v")) >= 0) {
+    switch (c) {
+      case 'b': o.best = (uint32_t)atoi(optarg); break;
+      case 'd': o.db = optarg; break;
+      case 'D': {
+        std::istringstream ss(optarg);
+        std::string tok;
+        while (std::getline(ss, tok, ',')) o.devices.push_back(atoi(tok.c_str()));
+        break;
+      }
+      case 'e': o.extend = (uint32_t)atoi(optarg); break;
+      case 'E': o.extend_gap = -1 * atoi(optarg); break;
+      case 'G': o.open_gap = -1 * atoi(optarg); break;
+      case 'i': o.queries = optarg; break;
+      case 'S': o.start_chunk = (uint32_t)atoi(optarg); break;
+      case 'L': o.end_chunk = (uint32_t)atoi(optarg); break;
+      case 'l': o.max_list_length = (uint32_t)(atoi(optarg) * (1 << 20)); break;
+      case 'M': o.matrix_file = optarg; break;
+      case 'o': o.output = optarg; break;
+      case 'r': {
+        int lr = (int)log2((double)atoi(optarg));
+        o.log_region = lr < 1 ? 1u : (uint32_t)lr;
+        break;
+      }
+      case 's': o.shift = (uint32_t)atoi(optarg); break;
+      case 't': o.threshold = (uint32_t)atoi(optarg); break;
+      case 'y': o.style = atoi(optarg); break;
+      case 'v': o.verbose = true; break;
+      default: throw std::invalid_argument("");
+    }
+  }
+  if (o.devices.empty()) o.devices.push_back(0);  // this build has no CPU path: default to GPU 0
+  return o;
+}
+
+void check(int rc, const char *what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + gm_last_error());
+}
+
+// ---- hit list exchange between devices, in db-chunk order -------------------------------------
+struct Baton {           // which db chunk may merge next, and the lists it starts from
+  std::mutex mu;
+  std::condition_variable cv;
+  uint32_t next_chunk = 0;
+  std::vector<gm_hit> hits;
+  std::vector<uint32_t> counts;
+  std::string error;
+};
+
+void device_worker(gm_context *ctx, const std::vector<int> &my_chunks, bool single_device, Baton *baton) {
+  try {
+    for (int c : my_chunks) {
+      check(gm_align_prepare(ctx, (uint32_t)c, nullptr), "gm_align_prepare");
+      std::unique_lock<std::mutex> lock(baton->mu);
+      baton->cv.wait(lock, [&] { return baton->next_chunk == (uint32_t)c || !baton->error.empty(); });
+      if (!baton->error.empty()) return;
+      if (!single_device && c > 0) check(gm_results_upload(ctx, baton->hits.data(), baton->counts.data()), "gm_results_upload");
+      check(gm_align_merge(ctx, nullptr), "gm_align_merge");
+      if (!single_device) check(gm_results_download(ctx, baton->hits.data(), baton->counts.data()), "gm_results_download");
+      baton->next_chunk = (uint32_t)c + 1;
+      baton->cv.notify_all();
+    }
+  } catch (std::exception &e) {
+    std::lock_guard<std::mutex> lock(baton->mu);
+    baton->error = e.what();
+    baton->cv.notify_all();
+  }
+}
+
+// ---- output (aligner.cpp:951-1012) -------------------------------------------------------------
+void write_hits(std::ostream &out, const Options &o, const QueryChunk &q, const std::vector<gm_hit> &hits,
+                const std::vector<uint32_t> &counts, uint32_t cap, const std::vector<DbChunk> &names,
+                uint64_t db_length, const Karlin &karlin) {
+  for (uint32_t i = 0; i < q.n; ++i) {
+    const std::string &qname = q.names[i];
+    uint64_t search_space = 0;
+    if (o.style == 0) {  // query length without the trailing X padding (aligner.cpp:956-963)
+      const uint32_t start = i * q.length, end = (i + 1) * q.length - 1;
+      uint32_t offset = end;
+      for (; offset > start && q.seqs[offset] == kBaseX; --offset) {}
+      search_space = (uint64_t)(offset - start + 1) * db_length;
+    }
+    for (uint32_t k = 0; k < counts[i]; ++k) {
+      const gm_hit &h = hits[(size_t)i * cap + k];
+      const std::string &dname = names[h.db_chunk].names[h.db_id];
+      if (o.style == 1) {
+        out << qname << "\t" << dname << "\t" << h.score << "\t" << h.db_start + 1 << "\t" << h.db_end + 1 << std::endl;
+      } else if (o.style == 2) {
+        out << qname << "\t" << dname << "\t" << h.score << "\t" << h.db_start + 1 << "\t" << h.db_end + 1 << "\t"
+            << h.seq_id << "\t" << h.aln_len << "\t" << h.aln_match << std::endl;
+      } else {
+        const float bits = bit_score((int)h.score, karlin);
+        const float ev = (float)e_value((int)h.score, search_space, karlin);  // stored as float, aligner.cpp:966
+        out << qname << "\t" << dname << "\t" << h.seq_id * 100 << "\t" << h.aln_len << "\t" << h.aln_match << "\t"
+            << h.db_start + 1 << "\t" << h.db_end + 1 << "\t" << ev << "\t" << bits << "\t" << std::endl;
+      }
+    }
+  }
+}
+
+int run_aln(int argc, char **argv) {
+  Options o = parse_options(argc, argv);
+  const ScoreMatrix sm = load_matrix(o.matrix_file);
+  Karlin karlin = {0, 0, 0};
+  if (o.style == 0) karlin = gapped_karlin(sm, o.open_gap, o.extend_gap);
+  std::ofstream out(o.output.c_str());
+  if (o.verbose) {
+    std::cout << "#     G H O S T M  (ghostm_b200, " << gm_version() << ")" << std::endl;
+    std::cout << "# * GPU-base HOmology Search Tool for Metagenomics *" << std::endl << std::endl;
+  }
+  DbInfo info;
+  if (!read_db_info(o.db, &info) || info.division <= 0) {
+    std::cerr << "[Aligner] error: don't find db file." << std::endl;
+    return 0;
+  }
+  const size_t n_dev = o.devices.size();
+  std::vector<gm_context *> ctx(n_dev, nullptr);
+  gm_options go;
+  memset(&go, 0, sizeof(go));
+  go.seed = info.seed;
+  go.shift = o.shift;
+  go.log_region = o.log_region;
+  go.threshold = o.threshold;
+  go.extend = o.extend;
+  go.best = o.best;
+  go.max_list_length = o.max_list_length;
+  go.open_gap = o.open_gap;
+  go.extend_gap = o.extend_gap;
+  memcpy(go.score_matrix, sm.m, sizeof(go.score_matrix));
+  for (size_t d = 0; d < n_dev; ++d) {
+    check(gm_create(o.devices[d], &ctx[d]), "gm_create");
+    check(gm_set_options(ctx[d], &go), "gm_set_options");
+    check(gm_set_deferred_traceback(ctx[d], n_dev == 1), "gm_set_deferred_traceback");
+  }
+  // db chunks: resident for the whole run (the reference re-reads them per query chunk)
+  std::vector<DbChunk> names(info.division);
+  std::vector<std::vector<int>> owned(n_dev);
+  for (int c = 0; c < info.division; ++c) {
+    DbChunk full;
+    if (!read_db_chunk(o.db, c, &full, true)) {
+      std::cerr << "[Aligner] error: don't find db file." << std::endl;
+      return 0;
+    }
+    const size_t d = (size_t)c % n_dev;
+    check(gm_db_upload(ctx[d], (uint32_t)c, full.seq.data(), full.seq_len, full.keys_count.data(),
+                       (uint32_t)full.keys_count.size(), full.positions.data(), (uint32_t)full.positions.size(),
+                       full.seq_starts.data(), full.n_seqs), "gm_db_upload");
+    owned[d].push_back(c);
+    names[c].names.swap(full.names);
+    if (o.verbose) std::cout << "  db chunk " << c << " -> device " << o.devices[d] << std::endl;
+  }
+  // query chunks (query_reader.cpp:50-101, aligner.cpp:98-104,201-203)
+  std::ifstream qinf((o.queries + ".inf").c_str(), std::ios::binary);
+  int32_t q_division = 0;
+  if (qinf) qinf.read(reinterpret_cast<char *>(&q_division), 4);
+  uint32_t qi = o.start_chunk == UINT32_MAX ? 0u : o.start_chunk;
+  QueryChunk q;
+  if (q_division <= 0 || qi >= (uint32_t)q_division || !read_query_chunk(o.queries, qi, &q)) {
+    std::cerr << "[Aligner] error: don't find query file." << std::endl;
+  } else {
+    const uint32_t cap = o.best > 1 ? o.best : 1;
+    while (true) {
+      std::vector<uint8_t> name_break(q.n, 0);
+      for (uint32_t i = 1; i < q.n; ++i) name_break[i] = q.names[i] != q.names[i - 1];
+      uint64_t budget = std::min<uint64_t>((uint64_t)q.n * 2048 + (1u << 22), (1ull << 32) - 1);
+      for (size_t d = 0; d < n_dev; ++d) {
+        check(gm_set_candidate_capacity(ctx[d], budget), "gm_set_candidate_capacity");
+        check(gm_query_upload(ctx[d], q.seqs.data(), q.n, q.length, name_break.data()), "gm_query_upload");
+      }
+      Baton baton;
+      baton.hits.assign((size_t)q.n * cap, gm_hit());
+      baton.counts.assign(q.n, 0);
+      std::vector<std::thread> workers;
+      for (size_t d = 0; d < n_dev; ++d)
+        workers.emplace_back(device_worker, ctx[d], std::cref(owned[d]), n_dev == 1, &baton);
+      for (auto &w : workers) w.join();
+      if (!baton.error.empty()) throw std::runtime_error(baton.error);
+      if (n_dev == 1) {
+        check(gm_results_download(ctx[0], baton.hits.data(), baton.counts.data()), "gm_results_download");
+      } else {
+        // TraceBack ran inside every Merge on the owning device: the last lists are complete
+      }
+      write_hits(out, o, q, baton.hits, baton.counts, cap, names, (uint32_t)info.sum_length, karlin);
+      ++qi;  // aligner.cpp:201-203
+      if (qi > o.end_chunk || qi >= (uint32_t)q_division || !read_query_chunk(o.queries, qi, &q)) break;
+    }
+  }
+  for (auto *c : ctx) gm_destroy(c);
+  out.close();
+  if (o.verbose) std::cout << "Complete." << std::endl;
+  return 0;
+}
+
+void usage() {
+  std::cerr << "usage: ghostm_b200 aln [-i queries] [-d database] [-o output] [-D device[,device...]]\n"
+               "          [-v] [-b best] [-G openGap] [-E extendGap] [-M scoreMatrix] [-l candidatesMB]\n"
+               "          [-s skip] [-t threshold] [-r regionSize] [-e extendSize] [-S first] [-L last] [-y style]\n"
+               "   `db` and `qry` formatting stay with the reference tool; the file formats are unchanged.\n";
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 2 || strcmp(argv[1], "aln") != 0) {
+    usage();
+    return 1;
+  }
+  try {  // main.cpp:107-121: errors are reported, the exit status stays 0 like the reference
+    return run_aln(argc - 1, argv + 1);
+  } catch (std::exception &e) {
+    std::cerr << "error: " << e.what() << std::endl;
+    return 0;
+  }
+}

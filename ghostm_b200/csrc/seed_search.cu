@@ -262,10 +262,12 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_kernel(const Se
 //     HBM latency of the next tile hides behind the passes of the current one;
 //   * per tile 3 block barriers; ordered compaction of the sparse emit bitmap by one warp.
 constexpr int kTileBatch = 16;
+constexpr int kFastThreads = 512;        // two CTAs per SM: one CTA's barrier/latency phases overlap
+constexpr int kFastWarps = kFastThreads / 32;   // with the other CTA's issue slots
 constexpr int kSlots = 8;                // register-resident chunks per warp per tile
 constexpr int kFastLists = 64;
 constexpr int kChunk = 31;               // new positions per chunk (lane 0 carries the predecessor)
-constexpr int kChunkTable = kSlots * kSearchWarps;   // chunks per tile with a list-id table entry
+constexpr int kChunkTable = kSlots * kFastWarps;   // chunks per tile with a list-id table entry
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 struct FastShared {
@@ -274,7 +276,7 @@ struct FastShared {
   uint32_t fr[kTileBatch + 1][kFastLists];        // region of that position (kNone: none left)
   uint32_t pre[kTileBatch][kFastLists + 1];       // exclusive prefix of chunks per list
   uint8_t chunk_list[kTileBatch][kChunkTable];    // chunk k -> list (k < kChunkTable)
-  uint32_t scan[kSearchWarps];
+  uint32_t scan[32];
   uint32_t min_d, max_d;
   uint32_t query, out_n;
   unsigned long long base;
@@ -323,7 +325,7 @@ __device__ __forceinline__ void arrive(uint32_t *planes, uint32_t words, uint32_
 }
 
 template <int T>
-__global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const SearchParams p) {
   extern __shared__ __align__(16) uint32_t dyn[];
   __shared__ FastShared sh;
   const uint32_t M = p.tile_regions;
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
   uint32_t *staging = p.staging + (size_t)blockIdx.x * p.staging_cap;
   const uint32_t r = p.log_region;
 
-  for (uint32_t i = tid; i < (T + 1) * words + groups / 32 + 1; i += kSearchThreads) dyn[i] = 0;
+  for (uint32_t i = tid; i < (T + 1) * words + groups / 32 + 1; i += kFastThreads) dyn[i] = 0;
   if (tid == 0) sh.visited = 0;
   __syncthreads();
 
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
         for (uint32_t batch0 = tile_first; batch0 <= tile_last; batch0 += kTileBatch) {
           const uint32_t n_tiles = min((uint32_t)kTileBatch, tile_last - batch0 + 1);
           // ---- slice boundaries of this batch: binary search per (list, boundary)
-          for (uint32_t i = tid; i < (n_tiles + 1) * p.list_len; i += kSearchThreads) {
+          for (uint32_t i = tid; i < (n_tiles + 1) * p.list_len; i += kFastThreads) {
             const uint32_t t = i / p.list_len, j = i - t * p.list_len;
             const uint32_t off = j * p.shift;
             const unsigned long long target = (unsigned long long)(batch0 + t) * M;  // region
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
             sh.pre[tid][p.list_len] = acc;
           }
           __syncthreads();
-          for (uint32_t i = tid; i < n_tiles * p.list_len; i += kSearchThreads) {
+          for (uint32_t i = tid; i < n_tiles * p.list_len; i += kFastThreads) {
             const uint32_t t = i / p.list_len, j = i - t * p.list_len;
             const uint32_t k1 = min(sh.pre[t][j + 1], (uint32_t)kChunkTable);
             for (uint32_t k = sh.pre[t][j]; k < k1; ++k) sh.chunk_list[t][k] = (uint8_t)j;
@@ -413,8 +415,9 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
             const uint32_t total = sh.pre[t][p.list_len];
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) {
-              const uint32_t k = warp + 32 * s;
-              nxt[s] = k < total ? load_chunk(p, sh, t, k, lane) : kNone;
+              const uint32_t k = warp + kFastWarps * s;
+              if (k >= total) break;
+              nxt[s] = load_chunk(p, sh, t, k, lane);
             }
           }
           while (t < n_tiles) {
@@ -423,9 +426,12 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
             // ---- marks of this tile (run starts), from the loaded chunks
             uint32_t mark[kSlots];
 #pragma unroll
+            for (int s = 0; s < kSlots; ++s) mark[s] = kNone;
+#pragma unroll
             for (int s = 0; s < kSlots; ++s) {
-              const uint32_t k = warp + 32 * s;
-              mark[s] = k < total ? chunk_mark(p, sh, t, k, lane, nxt[s], base) : kNone;
+              const uint32_t k = warp + kFastWarps * s;
+              if (k >= total) break;
+              mark[s] = chunk_mark(p, sh, t, k, lane, nxt[s], base);
             }
             // ---- next non-empty tile: issue its loads now (latency hides behind the passes)
             uint32_t tn = t + 1;
@@ -434,8 +440,9 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
               const uint32_t total_n = sh.pre[tn][p.list_len];
 #pragma unroll
               for (int s = 0; s < kSlots; ++s) {
-                const uint32_t k = warp + 32 * s;
-                nxt[s] = k < total_n ? load_chunk(p, sh, tn, k, lane) : kNone;
+                const uint32_t k = warp + kFastWarps * s;
+                if (k >= total_n) break;
+                nxt[s] = load_chunk(p, sh, tn, k, lane);
               }
             }
             // ---- pass 1: arrive
@@ -443,7 +450,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
             for (int s = 0; s < kSlots; ++s)
               if (mark[s] != kNone) arrive<T>(planes, words, mark[s]);
             // chunks beyond the register slots (very dense tiles): streamed, re-read per pass
-            for (uint32_t k = warp + 32 * kSlots; k < total; k += 32) {
+            for (uint32_t k = warp + kFastWarps * kSlots; k < total; k += kFastWarps) {
               const uint32_t x = chunk_mark(p, sh, t, k, lane, load_chunk(p, sh, t, k, lane), base);
               if (x != kNone) arrive<T>(planes, words, x);
             }
@@ -468,7 +475,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
                 atomicOr(&summary[w >> 10], 1u << ((w >> 5) & 31));
               }
             }
-            for (uint32_t k = warp + 32 * kSlots; k < total; k += 32) {
+            for (uint32_t k = warp + kFastWarps * kSlots; k < total; k += kFastWarps) {
               const uint32_t x = chunk_mark(p, sh, t, k, lane, load_chunk(p, sh, t, k, lane), base);
               if (x != kNone && emits<T>(planes, words, x)) {
                 const uint32_t w = x >> 5;
@@ -487,7 +494,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
                 for (int tt = 0; tt < T; ++tt) planes[tt * words + (x >> 5)] = 0;
               }
             }
-            for (uint32_t k = warp + 32 * kSlots; k < total; k += 32) {
+            for (uint32_t k = warp + kFastWarps * kSlots; k < total; k += kFastWarps) {
               const uint32_t x = chunk_mark(p, sh, t, k, lane, load_chunk(p, sh, t, k, lane), base);
               if (x != kNone) {
 #pragma unroll
@@ -506,7 +513,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
             __syncthreads();  // B2
             // ---- compaction step 2: ordered write
             {
-              const uint32_t mine = sh.scan[lane];
+              const uint32_t mine = lane < kFastWarps ? sh.scan[lane] : 0u;
               uint32_t before = __reduce_add_sync(kFull, lane < warp ? mine : 0u) + sh.out_n;
               const uint32_t all = __reduce_add_sync(kFull, mine);
               for (uint32_t gb = my_groups; gb; gb &= gb - 1) {
@@ -555,7 +562,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_fast_kernel(con
         }
         if (!fits || n == 0) break;
         if (n <= p.staging_cap) {
-          for (uint32_t i = tid; i < n; i += kSearchThreads) p.cand_start[cbase + i] = staging[i];
+          for (uint32_t i = tid; i < n; i += kFastThreads) p.cand_start[cbase + i] = staging[i];
           break;
         }
         out = p.cand_start + cbase;   // more candidates than the staging area: redo in place
@@ -576,9 +583,15 @@ size_t search_smem_bytes(int T, uint32_t M) {
 
 }  // namespace
 
+bool search_uses_fast(uint32_t list_len, bool allow_fast) { return allow_fast && list_len <= kFastLists; }
+
 // Largest tile (multiple of 1024 regions, at most 1024 groups) that fits `smem_limit`.
-uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions) {
+uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions, bool fast) {
   uint32_t m = 1024u * 1024u;
+  if (fast) {  // two CTAs per SM, at most kFastWarps summary words (32 groups of 1024 regions each)
+    smem_limit = smem_limit / 2 - 2048;
+    m = kFastWarps * 32u * 1024u;
+  }
   while (m > 1024 && search_smem_bytes(T, m) + sizeof(SearchShared) + 256 > smem_limit) m -= 1024;
   while (m > 1024 && search_smem_bytes(T, m) + sizeof(FastShared) + 256 > smem_limit) m -= 1024;
   const uint32_t need = ((n_regions + 1023) / 1024) * 1024;
@@ -588,7 +601,7 @@ uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions) {
 cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream, bool allow_fast) {
   const int T = (int)p.threshold;
   const size_t smem = search_smem_bytes(T, p.tile_regions);
-  const bool fast = allow_fast && p.list_len <= kFastLists;
+  const bool fast = search_uses_fast(p.list_len, allow_fast);
   cudaError_t err = cudaSuccess;
 #define GM_LAUNCH_SEARCH(TT)                                                                   \
   case TT:                                                                                     \
@@ -596,7 +609,7 @@ cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t str
       err = cudaFuncSetAttribute(seed_search_fast_kernel<TT>,                                  \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
       if (err != cudaSuccess) return err;                                                      \
-      seed_search_fast_kernel<TT><<<grid, kSearchThreads, smem, stream>>>(p);                  \
+      seed_search_fast_kernel<TT><<<grid * 2, kFastThreads, smem, stream>>>(p);                  \
     } else {                                                                                   \
       err = cudaFuncSetAttribute(seed_search_kernel<TT>,                                       \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \

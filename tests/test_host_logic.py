@@ -132,7 +132,8 @@ def test_chunks_of_rank_partition():
     for n in (1, 3, 8, 9):
         for w in (1, 2, 4, 8):
             parts = [ring.chunks_of_rank(n, r, w) for r in range(w)]
-            assert sum(parts, []) == list(range(n))
+            assert sorted(sum(parts, [])) == list(range(n))
+            assert all(c % w == r for r, p in enumerate(parts) for c in p)
 
 
 _RING_WORKER = r"""
@@ -167,7 +168,7 @@ class OracleEngine(ring.Engine):
         return self.t_hits, self.t_counts
 
 eng = OracleEngine()
-final = ring.ring_step(eng, dist, rank, world, ring.chunks_of_rank(len(db.chunks), rank, world))
+final = ring.ring_step(eng, dist, rank, world, len(db.chunks))
 if final:
     single = O.align_chunk(qc, db, opt)
     assert np.array_equal(single.counts, eng.res.counts)
