@@ -641,7 +641,7 @@ extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *s
   uint32_t launches = 0;
   if (!c->use_s32) {
     if (n_strips > 1) {
-      const size_t need = (size_t)c->sm_count * kSwWarps * p.base_len * 96;
+      const size_t need = (size_t)c->sm_count * 2 * kSwWarps * p.base_len * 96;  // up to 2 CTAs per SM
       GM_CUDA(c->strip_scratch.ensure(need));
     }
     p.strip_scratch = c->strip_scratch.p;

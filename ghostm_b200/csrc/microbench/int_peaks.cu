@@ -10,6 +10,7 @@
 // (32 x warp instructions / elapsed SM clocks), measured with clock64() inside the
 // kernel (max over CTAs), and Gops/s from CUDA events.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -22,14 +23,14 @@ constexpr int ITERS = 4096;
 constexpr int CHAINS = 8;
 
 enum Op { VIADDMNMX16 = 0, VIMNMX3_16, VIMNMX16, VIADD16, IADD32, IMAD32, LOP3, PRMT_OP,
-          MIX_DPX_IMAD, MIX_DPX_LDS, VIADDMNMX32, MIX_SWCELL, NUM_OPS };
+          MIX_DPX_IMAD, MIX_DPX_LDS, VIADDMNMX32, MIX_SWCELL, HMNMX2_OP, MIX_DPX_HMNMX2, HADD2_OP, MIX_DPX_HADD2, NUM_OPS };
 
 static const char *kNames[NUM_OPS] = {
   "viaddmnmx_s16x2", "vimnmx3_s16x2", "vimnmx_s16x2", "viadd_16x2", "iadd3_s32", "imad_s32",
   "lop3", "prmt", "mix_viaddmnmx16_imad_1to1", "mix_viaddmnmx16_lds_4to1", "viaddmnmx_s32",
-  "mix_swcell_5dpx_1prmt" };
+  "mix_swcell_5dpx_1prmt", "hmnmx2", "mix_viaddmnmx16_hmnmx2_1to1", "hadd2", "mix_viaddmnmx16_hadd2_1to1" };
 // instructions counted per chain step
-static const int kInstrPerStep[NUM_OPS] = {1, 1, 1, 1, 1, 1, 1, 1, 2, 5, 1, 6};
+static const int kInstrPerStep[NUM_OPS] = {1, 1, 1, 1, 1, 1, 1, 1, 2, 5, 1, 7, 1, 2, 1, 2};
 
 template <int OP>
 __global__ void __launch_bounds__(1024) rate_kernel(unsigned *out, unsigned a, unsigned b, unsigned c,
@@ -63,6 +64,24 @@ __global__ void __launch_bounds__(1024) rate_kernel(unsigned *out, unsigned a, u
         acc[i] = __viaddmax_s16x2(acc[i], b, c);
         acc[i] = __viaddmax_s16x2(acc[i], c, a);
         acc[i] = __viaddmax_s16x2(acc[i], a, b);
+      } else if (OP == HMNMX2_OP) {
+        __half2 x = *reinterpret_cast<__half2 *>(&acc[i]), y = *reinterpret_cast<__half2 *>(&acc[(i + 3) % CHAINS]);
+        __half2 r = __hmax2(x, y);
+        acc[i] = *reinterpret_cast<unsigned *>(&r) + 1u;
+      } else if (OP == MIX_DPX_HMNMX2) {
+        acc[i] = __viaddmax_s16x2(acc[i], a, b);
+        __half2 x = *reinterpret_cast<__half2 *>(&acc[(i + 4) % CHAINS]), y = *reinterpret_cast<__half2 *>(&c);
+        __half2 r = __hmax2(x, y);
+        acc[(i + 4) % CHAINS] = *reinterpret_cast<unsigned *>(&r);
+      } else if (OP == HADD2_OP) {
+        __half2 x = *reinterpret_cast<__half2 *>(&acc[i]), y = *reinterpret_cast<__half2 *>(&a);
+        __half2 r = __hadd2(x, y);
+        acc[i] = *reinterpret_cast<unsigned *>(&r);
+      } else if (OP == MIX_DPX_HADD2) {
+        acc[i] = __viaddmax_s16x2(acc[i], a, b);
+        __half2 x = *reinterpret_cast<__half2 *>(&acc[(i + 4) % CHAINS]), y = *reinterpret_cast<__half2 *>(&c);
+        __half2 r = __hadd2(x, y);
+        acc[(i + 4) % CHAINS] = *reinterpret_cast<unsigned *>(&r);
       } else if (OP == MIX_SWCELL) {
         // the dependency shape of one packed SW cell: E, a, m, F(chain), H, colmax + 1 PRMT
         unsigned e = __viaddmax_s16x2(acc[i], a, acc[(i + 1) % CHAINS]);
@@ -127,6 +146,10 @@ int main() {
   run<MIX_DPX_IMAD>(sms, T, C, d_out, d_cyc, 0);
   run<MIX_DPX_LDS>(sms, T, C, d_out, d_cyc, 0);
   run<MIX_SWCELL>(sms, T, C, d_out, d_cyc, 0);
+  run<HMNMX2_OP>(sms, T, C, d_out, d_cyc, 0);
+  run<MIX_DPX_HMNMX2>(sms, T, C, d_out, d_cyc, 0);
+  run<HADD2_OP>(sms, T, C, d_out, d_cyc, 0);
+  run<MIX_DPX_HADD2>(sms, T, C, d_out, d_cyc, 0);
   // low-occupancy points (what a 200-register kernel gets): 256 threads/SM
   run<VIADDMNMX16>(sms, 256, 1, d_out, d_cyc, 0);
   run<MIX_SWCELL>(sms, 256, 1, d_out, d_cyc, 0);

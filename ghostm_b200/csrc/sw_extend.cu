@@ -20,6 +20,8 @@
 //    masks the affected half; queries longer than R rows run as horizontal strips whose
 //    boundary row (H+open, F, column max) goes through an L2-resident scratch.
 //  * scores fit s16: the host refuses option sets where L * max(matrix) could overflow.
+#include <stdlib.h>
+
 #include "gm_common.cuh"
 
 namespace gm {
@@ -31,7 +33,7 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 __device__ __forceinline__ uint32_t pack2(int v) { return (uint32_t)(v & 0xFFFF) * 0x10001u; }
 
 template <int R>
-__global__ void __launch_bounds__(kSwThreads, 1) sw_extend_dpx_kernel(const SwParams p) {
+__global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_kernel(const SwParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int16_t *matT = reinterpret_cast<int16_t *>(smem_raw);                 // [query residue][db residue]
   uint16_t *prof_all = reinterpret_cast<uint16_t *>(smem_raw + 2048);    // per warp [R][32]
@@ -225,7 +227,7 @@ cudaError_t launch_dpx(const SwParams &p, int sm_count, cudaStream_t stream) {
   cudaError_t err = cudaFuncSetAttribute(sw_extend_dpx_kernel<R>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  sw_extend_dpx_kernel<R><<<sm_count, kSwThreads, smem, stream>>>(p);
+  sw_extend_dpx_kernel<R><<<sm_count * (R <= 40 ? 2 : 1), kSwThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -234,7 +236,12 @@ cudaError_t launch_dpx(const SwParams &p, int sm_count, cudaStream_t stream) {
 // rows per strip for a query length: the smallest instantiated R that covers L in
 // ceil(L / kSwMaxRows) strips.
 int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips) {
-  static const int kRows[] = {16, 32, 48, 64, 75, 80};
+  static const int kRows[] = {16, 32, 40, 48, 64, 75, 80};
+  if (const char *env = getenv("GM_SW_ROWS")) {  // tuning experiments: force rows per strip
+    const int r = atoi(env);
+    for (int k : kRows)
+      if (k == r) { *n_strips = (query_len + r - 1) / r; return r; }
+  }
   const uint32_t strips = (query_len + kSwMaxRows - 1) / kSwMaxRows;
   const uint32_t need = (query_len + strips - 1) / strips;
   for (int r : kRows)
@@ -247,6 +254,7 @@ cudaError_t sw_extend_launch(const SwParams &p, int rows, int sm_count, cudaStre
   switch (rows) {
     case 16: return launch_dpx<16>(p, sm_count, stream);
     case 32: return launch_dpx<32>(p, sm_count, stream);
+    case 40: return launch_dpx<40>(p, sm_count, stream);
     case 48: return launch_dpx<48>(p, sm_count, stream);
     case 64: return launch_dpx<64>(p, sm_count, stream);
     case 75: return launch_dpx<75>(p, sm_count, stream);
