@@ -289,7 +289,12 @@ def run_ours(a):
             "gpu_launches": int(launches),
             "roofline": {"bound": "int_dpx", "kernel": "sw_extend_dpx_kernel<75>",
                          "achieved": achieved, "peak": peak, "unit": "Tint-op/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None,
+                         # dram__bytes_read+write of one `ncu --set full` capture of this kernel
+                         # (profiles/r1_sw_extend_ncu.md: 611.0 MB for 5,595,674 candidates),
+                         # scaled to the candidates of one launch of this run
+                         "traffic": 611.0e6 / 5595674 * (st["candidates"] / max(a.steps * len(mine), 1)),
+                         "algorithmic_bytes": (a.length + 36 + 12) * (st["candidates"] / max(a.steps * len(mine), 1)),
                          "note": "achieved = SW cells x 10 int ops / SW kernel time (CUDA events, "
                                  "rank 0); peak = measured VIADDMNMX.S16x2 issue rate x 4 ops "
                                  "(gm_measure_dpx_peak, same process)",

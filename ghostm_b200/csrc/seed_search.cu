@@ -279,6 +279,7 @@ struct FastShared {
   uint32_t scan[32];
   uint32_t min_d, max_d;
   uint32_t query, out_n;
+  uint32_t r1_double;   // one-pass variant: region 1 was hit twice (virtual region 0 rule)
   unsigned long long base;
   unsigned long long visited;
 };
@@ -324,14 +325,45 @@ __device__ __forceinline__ void arrive(uint32_t *planes, uint32_t words, uint32_
     if (old & bit) old = atomicOr(&planes[tt * words + w], bit); else break;
 }
 
-template <int T>
+// threshold 2 in ONE pass: cnt(d) + cnt(d+1) >= 2 with cnt(d) >= 1 holds iff two marks hit d, or
+// one hits d and one hits d+1.  Whichever of the two marks arrives LATER sees the other's bit in
+// the value returned by its own atomicOr (or, across a word boundary, in an ordered atomic read
+// issued after it), so the decision is taken at arrival time: no second count plane, no decide
+// pass.  Setting the emit bit is idempotent.  A halo mark (region base+M) only vouches for its
+// left neighbour.  Returns true on a double arrival at x.
+__device__ __forceinline__ bool arrive_decide(uint32_t *p0, uint32_t *emitb, uint32_t *summary,
+                                              uint32_t x, bool halo) {
+  const uint32_t w = x >> 5, b = x & 31, bit = 1u << b;
+  const uint32_t old = atomicOr(&p0[w], bit);
+  bool self = false, left = false;
+  if (!halo) {
+    self = (old & bit) != 0;
+    self |= b < 31 ? ((old >> (b + 1)) & 1u) != 0 : (atomicOr(&p0[w + 1], 0u) & 1u) != 0;
+  }
+  if (b > 0) left = ((old >> (b - 1)) & 1u) != 0;
+  else if (w > 0) left = (atomicOr(&p0[w - 1], 0u) >> 31) != 0;
+  if (self) {
+    atomicOr(&emitb[w], bit);
+    atomicOr(&summary[w >> 10], 1u << ((w >> 5) & 31));
+  }
+  if (left) {
+    const uint32_t y = x - 1, wy = y >> 5;
+    atomicOr(&emitb[wy], 1u << (y & 31));
+    atomicOr(&summary[wy >> 10], 1u << ((wy >> 5) & 31));
+  }
+  return !halo && (old & bit) != 0;
+}
+
+template <int T, bool ONEPASS>
 __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const SearchParams p) {
+  static_assert(!ONEPASS || T == 2, "the one-pass decision is the threshold-2 identity");
+  constexpr int NP = ONEPASS ? 1 : T;   // count planes
   extern __shared__ __align__(16) uint32_t dyn[];
   __shared__ FastShared sh;
   const uint32_t M = p.tile_regions;
   const uint32_t words = M / 32 + 1;
   uint32_t *planes = dyn;
-  uint32_t *emitb = dyn + T * words;
+  uint32_t *emitb = dyn + NP * words;
   uint32_t *summary = emitb + words;
   const uint32_t groups = M / 1024;
   const uint32_t n_sw = (groups + 31) / 32;       // <= 32 summary words, one per warp
@@ -339,7 +371,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
   uint32_t *staging = p.staging + (size_t)blockIdx.x * p.staging_cap;
   const uint32_t r = p.log_region;
 
-  for (uint32_t i = tid; i < (T + 1) * words + groups / 32 + 1; i += kFastThreads) dyn[i] = 0;
+  for (uint32_t i = tid; i < (NP + 1) * words + groups / 32 + 1; i += kFastThreads) dyn[i] = 0;
   if (tid == 0) sh.visited = 0;
   __syncthreads();
 
@@ -353,7 +385,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
     uint32_t *out = staging;
     uint32_t out_cap = p.staging_cap;
     for (int attempt = 0; attempt < 2; ++attempt) {
-      if (tid == 0) { sh.min_d = kNone; sh.max_d = 0; sh.out_n = 0; }
+      if (tid == 0) { sh.min_d = kNone; sh.max_d = 0; sh.out_n = 0; sh.r1_double = 0; }
       __syncthreads();
       if (tid < p.list_len) {
         const uint32_t j = tid, off = j * p.shift;
@@ -448,34 +480,51 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
             // ---- pass 1: arrive
 #pragma unroll
             for (int s = 0; s < kSlots; ++s)
-              if (mark[s] != kNone) arrive<T>(planes, words, mark[s]);
+              if (mark[s] != kNone) {
+                if (ONEPASS) {
+                  if (arrive_decide(planes, emitb, summary, mark[s], false) && base + mark[s] == 1)
+                    sh.r1_double = 1;
+                } else {
+                  arrive<T>(planes, words, mark[s]);
+                }
+              }
             // chunks beyond the register slots (very dense tiles): streamed, re-read per pass
             for (uint32_t k = warp + kFastWarps * kSlots; k < total; k += kFastWarps) {
               const uint32_t x = chunk_mark(p, sh, t, k, lane, load_chunk(p, sh, t, k, lane), base);
-              if (x != kNone) arrive<T>(planes, words, x);
+              if (x != kNone) {
+                if (ONEPASS) {
+                  if (arrive_decide(planes, emitb, summary, x, false) && base + x == 1) sh.r1_double = 1;
+                } else {
+                  arrive<T>(planes, words, x);
+                }
+              }
             }
             // halo: the first position of region base+M of every list counts for region base+M-1
-            if (tid < p.list_len && sh.fr[t + 1][tid] == base + M) arrive<T>(planes, words, M);
+            if (tid < p.list_len && sh.fr[t + 1][tid] == base + M) {
+              if (ONEPASS) arrive_decide(planes, emitb, summary, M, true);
+              else arrive<T>(planes, words, M);
+            }
             __syncthreads();  // A
             if (tid == 0 && batch0 + t == 0) {
               // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an
               // unoccupied region 0 still emits when region 1 alone reaches the threshold.
-              if (!(planes[0] & 1u) && (planes[(T - 1) * words] & 2u)) {
+              const bool r1 = ONEPASS ? sh.r1_double != 0 : (planes[(NP - 1) * words] & 2u) != 0;
+              if (!(planes[0] & 1u) && r1) {
                 atomicOr(&emitb[0], 1u);
                 atomicOr(&summary[0], 1u);
               }
             }
-            // ---- pass 2: decide
+            // ---- pass 2: decide (multi-plane variant only)
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) {
               const uint32_t x = mark[s];
-              if (x != kNone && emits<T>(planes, words, x)) {
+              if (!ONEPASS && x != kNone && emits<T>(planes, words, x)) {
                 const uint32_t w = x >> 5;
                 atomicOr(&emitb[w], 1u << (x & 31));
                 atomicOr(&summary[w >> 10], 1u << ((w >> 5) & 31));
               }
             }
-            for (uint32_t k = warp + kFastWarps * kSlots; k < total; k += kFastWarps) {
+            for (uint32_t k = warp + kFastWarps * kSlots; !ONEPASS && k < total; k += kFastWarps) {
               const uint32_t x = chunk_mark(p, sh, t, k, lane, load_chunk(p, sh, t, k, lane), base);
               if (x != kNone && emits<T>(planes, words, x)) {
                 const uint32_t w = x >> 5;
@@ -483,7 +532,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
                 atomicOr(&summary[w >> 10], 1u << ((w >> 5) & 31));
               }
             }
-            __syncthreads();  // B
+            if (!ONEPASS) __syncthreads();  // B (the one-pass variant has nothing between A and the clear)
             // ---- pass 3: clear; compaction step 1: every warp counts the emit bits of the
             // groups of "its" summary word
 #pragma unroll
@@ -491,17 +540,17 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
               const uint32_t x = mark[s];
               if (x != kNone) {
 #pragma unroll
-                for (int tt = 0; tt < T; ++tt) planes[tt * words + (x >> 5)] = 0;
+                for (int tt = 0; tt < NP; ++tt) planes[tt * words + (x >> 5)] = 0;
               }
             }
             for (uint32_t k = warp + kFastWarps * kSlots; k < total; k += kFastWarps) {
               const uint32_t x = chunk_mark(p, sh, t, k, lane, load_chunk(p, sh, t, k, lane), base);
               if (x != kNone) {
 #pragma unroll
-                for (int tt = 0; tt < T; ++tt) planes[tt * words + (x >> 5)] = 0;
+                for (int tt = 0; tt < NP; ++tt) planes[tt * words + (x >> 5)] = 0;
               }
             }
-            if (tid < T) planes[tid * words + (M >> 5)] = 0;   // halo word
+            if (tid < NP) planes[tid * words + (M >> 5)] = 0;   // halo word
             const uint32_t my_groups = warp < n_sw ? summary[warp] : 0u;
             {
               uint32_t cnt = 0;
@@ -576,17 +625,20 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
 }
 
 // Generic dynamic shared memory size for a tile of M regions.
-size_t search_smem_bytes(int T, uint32_t M) {
+size_t search_smem_bytes(int planes, uint32_t M) {   // count planes + the emit bitmap + summary
   const uint32_t words = M / 32 + 1;
-  return ((size_t)(T + 1) * words + M / 1024 / 32 + 1) * sizeof(uint32_t);
+  return ((size_t)(planes + 1) * words + M / 1024 / 32 + 1) * sizeof(uint32_t);
 }
+
+int search_planes(int T, bool fast) { return (fast && T == 2) ? 1 : T; }
 
 }  // namespace
 
 bool search_uses_fast(uint32_t list_len, bool allow_fast) { return allow_fast && list_len <= kFastLists; }
 
 // Largest tile (multiple of 1024 regions, at most 1024 groups) that fits `smem_limit`.
-uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions, bool fast) {
+uint32_t search_tile_regions(int T_in, size_t smem_limit, uint32_t n_regions, bool fast) {
+  const int T = search_planes(T_in, fast);
   uint32_t m = 1024u * 1024u;
   if (fast) {  // two CTAs per SM, at most kFastWarps summary words (32 groups of 1024 regions each)
     smem_limit = smem_limit / 2 - 2048;
@@ -600,16 +652,16 @@ uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions, bool 
 
 cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream, bool allow_fast) {
   const int T = (int)p.threshold;
-  const size_t smem = search_smem_bytes(T, p.tile_regions);
   const bool fast = search_uses_fast(p.list_len, allow_fast);
+  const size_t smem = search_smem_bytes(search_planes(T, fast), p.tile_regions);
   cudaError_t err = cudaSuccess;
 #define GM_LAUNCH_SEARCH(TT)                                                                   \
   case TT:                                                                                     \
     if (fast) {                                                                                \
-      err = cudaFuncSetAttribute(seed_search_fast_kernel<TT>,                                  \
+      err = cudaFuncSetAttribute(seed_search_fast_kernel<TT, TT == 2>,                         \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
       if (err != cudaSuccess) return err;                                                      \
-      seed_search_fast_kernel<TT><<<grid * 2, kFastThreads, smem, stream>>>(p);                  \
+      seed_search_fast_kernel<TT, TT == 2><<<grid * 2, kFastThreads, smem, stream>>>(p);       \
     } else {                                                                                   \
       err = cudaFuncSetAttribute(seed_search_kernel<TT>,                                       \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
