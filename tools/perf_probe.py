@@ -11,12 +11,13 @@ ap.add_argument("--queries", type=int, default=16384)
 ap.add_argument("--length", type=int, default=75)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--repeat-db", action="store_true")
+ap.add_argument("--capacity", type=int, default=1 << 28)
 a = ap.parse_args()
 
 ctx = capi.Context(0)
 mat = workloads.blosum62()
 ctx.set_options(0xF, mat)
-ctx.set_candidate_capacity(1 << 28)
+ctx.set_candidate_capacity(a.capacity)
 t = time.time()
 src = None
 for c in range(a.chunks):
