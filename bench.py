@@ -9,8 +9,10 @@ Workload (BASELINE.json config 3): synthetic metagenomic reads, 75-aa queries ag
 1 G-residue protein db formatted like `ghostm db -l 120` (8 chunks), BLOSUM62, default options.
 One STEP = one batch of --queries queries through the whole path (seed search, candidate
 chunking, SW extension, Merge, TraceBack) against the WHOLE db.  The db chunks are resident in
-HBM and sharded by chunk over the N ranks (strong scaling: total work per step is fixed); the
-per-query hit lists travel rank to rank over NCCL send/recv (ghostm_b200/ring.py).
+HBM and sharded by chunk over the N ranks (strong scaling: total work per step is fixed): every
+rank searches and extends its own chunks for ALL queries, the scored candidates are exchanged by
+query slice (NCCL all-to-all) and every rank runs Merge + TraceBack for its slice of the queries
+over all chunks in ascending order (ghostm_b200/shard.py).
 
 value  = SW cells of the step / device time, inputs (db, index, queries) resident in HBM.
 e2e    = same through the C ABI with HOST buffers: queries H2D from pinned memory and hit lists
@@ -19,6 +21,7 @@ e2e    = same through the C ABI with HOST buffers: queries H2D from pinned memor
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import shutil
@@ -128,7 +131,7 @@ class _DevArray:
 
 def run_ours(a):
     import torch
-    from ghostm_b200 import capi, ring, workloads
+    from ghostm_b200 import capi, ring, shard, workloads
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -147,16 +150,27 @@ def run_ours(a):
     matrix = workloads.blosum62()
     ctx.set_options(0xF, matrix)                      # -k 4, aligner.cpp:227-245 defaults
     ctx.set_candidate_capacity(min(max(a.queries * 1200, 1 << 22), (1 << 32) - 1))
-    ctx.set_deferred_traceback(world == 1)            # all chunks resident -> trace survivors only
+    ctx.set_deferred_traceback(True)                  # TraceBack once, for the survivors only
+    sharded = world > 1
+    back_ctx = None
+    if sharded:    # Merge + TraceBack of this rank's query slice: residues + .pos of every chunk
+        back_ctx = capi.Context(local)
+        back_ctx.set_options(0xF, matrix)
+        back_ctx.set_candidate_capacity(min(max(a.queries * 1200, 1 << 22), (1 << 32) - 1))
 
     n_chunks = n_db_chunks(a)
-    mine = ring.chunks_of_rank(n_chunks, rank, world)
+    mine = shard.chunks_of_rank(n_chunks, rank, world)
     t_setup = time.time()
     source = None
     sample = None
-    for c in mine:
+    for c in range(n_chunks):
+        if c not in mine and not sharded and c != 0:
+            continue
         seq, starts = workloads.synth_chunk(1, c, chunk_bytes_of(a, c, n_chunks))
-        ctx.db_build_index(c, seq, starts, 0xF)
+        if c in mine:
+            ctx.db_build_index(c, seq, starts, 0xF)
+        if sharded:
+            back_ctx.db_upload_seq(c, seq, starts)
         if c == 0:
             source = seq[: 4 << 20].copy()
             cut = int(np.searchsorted(starts, int(a.cpu_sample_mib * (1 << 20))))
@@ -175,12 +189,20 @@ def run_ours(a):
         q_all = qd.cpu()
     q_pinned = q_all.pin_memory()
     cap = 10
-    hits_pinned = torch.empty((a.queries * cap * 9,), dtype=torch.int32).pin_memory()
-    counts_pinned = torch.empty((a.queries,), dtype=torch.int32).pin_memory()
+    bounds = shard.slice_bounds(None, a.queries, world)
+    base, stop = int(bounds[rank]), int(bounds[rank + 1])
+    hits_pinned = torch.empty(((stop - base) * cap * 9,), dtype=torch.int32).pin_memory()
+    counts_pinned = torch.empty((stop - base,), dtype=torch.int32).pin_memory()
     setup_s = time.time() - t_setup
 
     dpx_rate = ctx.measure_dpx_peak()
     stats = capi.GmStats()
+    stats_back = capi.GmStats()
+    front = back = None
+    if sharded:
+        front = shard.GpuFront(ctx, a.queries, min(max(a.queries * 1200, 1 << 22), (1 << 32) - 1),
+                               f"cuda:{local}", stats)
+        back = shard.GpuBack(back_ctx, stats_back)
 
     class GpuEngine(ring.Engine):
         def prepare(self, c):
@@ -200,18 +222,29 @@ def run_ours(a):
 
     engine = GpuEngine()
     stream = torch.cuda.ExternalStream(ctx.stream())
+    stream_end = torch.cuda.ExternalStream(back_ctx.stream()) if sharded else stream
 
     def step(s: int, e2e: bool):
         b = s % n_batches
-        if e2e:
-            ctx.query_upload_ptr(q_pinned[b].data_ptr(), a.queries, a.length)
-        else:
-            ctx.results_clear()
-        final = ring.ring_step(engine, dist, rank, world, n_chunks)
-        if world == 1:
+        if not sharded:
+            if e2e:
+                ctx.query_upload_ptr(q_pinned[b].data_ptr(), a.queries, a.length)
+            else:
+                ctx.results_clear()
+            ring.ring_step(engine, dist, rank, world, n_chunks)
             ctx.traceback_pending(stats)
-        if e2e and final:
-            ctx.results_download_ptr(hits_pinned.data_ptr(), counts_pinned.data_ptr())
+            if e2e:
+                ctx.results_download_ptr(hits_pinned.data_ptr(), counts_pinned.data_ptr())
+            return
+        if e2e:   # every rank needs all queries (front) and its own slice again (back)
+            ctx.query_upload_ptr(q_pinned[b].data_ptr(), a.queries, a.length)
+            back_ctx.query_upload_ptr(q_pinned[b][base:stop].data_ptr(), stop - base, a.length)
+        else:
+            back_ctx.results_clear()
+        shard.shard_step(front, back, dist, rank, world, n_chunks, bounds,
+                         before_back=torch.cuda.synchronize)
+        if e2e:
+            back_ctx.results_download_ptr(hits_pinned.data_ptr(), counts_pinned.data_ptr())
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,31 +253,41 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     def timed(e2e: bool):
-        nonlocal stats
         if not e2e:
             ctx.query_upload_ptr(q_pinned[0].data_ptr(), a.queries, a.length)
+            if sharded:
+                back_ctx.query_upload_ptr(q_pinned[0][base:stop].data_ptr(), stop - base, a.length)
         for s in range(a.warmup):
             step(s, e2e)
         barrier()
-        stats = capi.GmStats()
+        for st_ in (stats, stats_back):      # in place: the engines hold references
+            C.memset(C.byref(st_), 0, C.sizeof(st_))
+        if sharded:
+            front.launches = back.launches = 0
         sampler = ClockSampler(local) if rank == 0 else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record(stream)
         for s in range(a.steps):
             step(a.warmup + s, e2e)
-        ev1.record(stream)
+        ev1.record(stream_end)
         barrier()
         wall = time.perf_counter() - t0
         dev_ms = ev0.elapsed_time(ev1)
         clocks = sampler.stop() if sampler else None
         t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=f"cuda:{local}")
-        cells = torch.tensor([float(stats.cells), float(stats.candidates), float(stats.kernel_launches),
+        launches = stats.kernel_launches + stats_back.kernel_launches
+        if sharded:
+            launches += front.launches + back.launches
+        cells = torch.tensor([float(stats.cells), float(stats.candidates), float(launches),
                               float(stats.seed_positions)], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(cells, op=dist.ReduceOp.SUM)
-        return t.tolist(), cells.tolist(), stats.as_dict(), clocks
+        st = stats.as_dict()
+        for k in ("ms_merge", "ms_traceback", "tracebacks", "candidate_chunks"):
+            st[k] += getattr(stats_back, k)
+        return t.tolist(), cells.tolist(), st, clocks
 
     (dev_ms, wall_ms), (cells, cands, launches, positions), st, clocks = timed(False)
     (e_dev_ms, e_wall_ms), (e_cells, _, _, _), _, _ = timed(True)
@@ -276,16 +319,18 @@ def run_ours(a):
                             "BLOSUM62, ghostm aln defaults",
                 "queries_per_step": a.queries, "query_len": a.length,
                 "db_residues": a.db_residues, "db_chunks": n_chunks, "chunk_mib": a.chunk_mib,
-                "parallelism": f"db chunks sharded over {world} rank(s), hit lists ring over NCCL",
+                "parallelism": (f"db chunks (index) sharded over {world} rank(s) for search + SW; "
+                                "candidates all-to-all by query slice over NCCL; Merge + TraceBack "
+                                "per query slice" if sharded else "1 rank, all db chunks resident"),
                 "cache": "inputs larger than L2: every step streams the index positions and "
                          "windows of all db chunks (>=0.6 GB per chunk) from HBM",
-                "traceback": "deferred to survivors" if world == 1 else "inside every Merge",
+                "traceback": "deferred to survivors",
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e_wall_ms / a.steps,
                     "queries_per_s": a.queries / (e_wall_ms / a.steps * 1e-3),
-                    "h2d_bytes_per_step": int(a.queries * a.length) * world,
-                    "d2h_bytes_per_step": int(hits_pinned.numel() * 4 + counts_pinned.numel() * 4)},
+                    "h2d_bytes_per_step": int(a.queries * a.length) * (world + (1 if sharded else 0)),
+                    "d2h_bytes_per_step": int(a.queries * cap * 36 + a.queries * 4)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "int_dpx", "kernel": "sw_extend_dpx_kernel<75>",
                          "achieved": achieved, "peak": peak, "unit": "Tint-op/s",

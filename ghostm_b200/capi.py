@@ -25,7 +25,8 @@ EXTENDED_SYMBOLS = ["gm_version", "gm_last_error", "gm_device_count", "gm_create
                     "gm_db_build_index", "gm_db_download_index", "gm_results_clear",
                     "gm_results_device", "gm_stream", "gm_measure_dpx_peak",
                     "gm_set_deferred_traceback", "gm_traceback_pending", "gm_set_search_variant",
-                    "gm_align_prepare", "gm_align_merge"]
+                    "gm_align_prepare", "gm_align_merge", "gm_db_upload_seq", "gm_candidates_pack",
+                    "gm_candidates_import"]
 
 HIT_DTYPE = np.dtype([("query_id", "<u4"), ("db_id", "<u4"), ("db_chunk", "<u4"), ("score", "<u4"),
                       ("db_start", "<u4"), ("db_end", "<u4"), ("aln_len", "<u4"),
@@ -77,6 +78,9 @@ def load():
     L.gm_set_candidate_capacity.argtypes = [vp, C.c_uint64]
     L.gm_db_upload.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp,
                                C.c_uint32]
+    L.gm_db_upload_seq.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
+    L.gm_candidates_pack.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint64, vp]
+    L.gm_candidates_import.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint64]
     L.gm_db_release.argtypes = [vp, C.c_uint32]
     L.gm_query_upload.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
     L.gm_align_chunk.argtypes = [vp, C.c_uint32, C.POINTER(GmStats)]
@@ -184,6 +188,24 @@ class Context:
         st = np.ascontiguousarray(chunk.seq_starts, dtype=np.uint32)
         self._check(self.L.gm_db_upload(self.h, chunk_id, _ptr(seq), seq.shape[0], _ptr(kc),
                                         kc.shape[0], _ptr(ps), ps.shape[0], _ptr(st), st.shape[0]))
+
+    def db_upload_seq(self, chunk_id: int, seq: np.ndarray, seq_starts: np.ndarray):
+        """Sequence-only chunk (Merge/TraceBack side of a db-sharded run)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        st = np.ascontiguousarray(seq_starts, dtype=np.uint32)
+        self._check(self.L.gm_db_upload_seq(self.h, chunk_id, _ptr(seq), seq.shape[0], _ptr(st),
+                                            st.shape[0]))
+
+    def candidates_pack(self, bounds, counts_ptr: int, data_ptr: int, capacity_words: int) -> np.ndarray:
+        """gm_candidates_pack into DEVICE buffers (raw addresses) -> per-part totals (host)."""
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        totals = np.zeros(b.shape[0] - 1, dtype=np.uint64)
+        self._check(self.L.gm_candidates_pack(self.h, b.shape[0] - 1, _ptr(b), counts_ptr or None,
+                                              data_ptr or None, capacity_words, _ptr(totals)))
+        return totals
+
+    def candidates_import(self, chunk_id: int, counts_ptr: int, data_ptr: int, total: int):
+        self._check(self.L.gm_candidates_import(self.h, chunk_id, counts_ptr, data_ptr or None, total))
 
     def db_build_index(self, chunk_id: int, seq: np.ndarray, seq_starts: np.ndarray, seed: int):
         seq = np.ascontiguousarray(seq, dtype=np.uint8)

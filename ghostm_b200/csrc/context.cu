@@ -105,6 +105,29 @@ __global__ void gather_kernel(const uint32_t *cand_off, const uint32_t *cand_cnt
   }
 }
 
+// gm_candidates_pack: per-query candidate slices -> per-part [start | score | end] blocks in
+// reference order.  prefix[] is the exclusive scan of cand_cnt over all queries.
+__global__ void pack_kernel(const uint32_t *cand_off, const uint32_t *cand_cnt,
+                            const uint32_t *prefix, uint32_t n_q, const uint32_t *bounds,
+                            uint32_t n_parts, const uint32_t *start, const uint32_t *score,
+                            const uint32_t *end, uint32_t *out) {
+  for (uint32_t q = blockIdx.x; q < n_q; q += gridDim.x) {
+    uint32_t lo = 0, hi = n_parts;  // bounds[lo] <= q < bounds[hi]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (bounds[mid] <= q) lo = mid; else hi = mid;
+    }
+    const size_t part_base = prefix[bounds[lo]], m = prefix[bounds[lo + 1]] - part_base;
+    uint32_t *dst = out + 3 * part_base + (prefix[q] - part_base);
+    const uint32_t off = cand_off[q], cnt = cand_cnt[q];
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      dst[i] = start[off + i];
+      dst[m + i] = score[off + i];
+      dst[2 * m + i] = end[off + i];
+    }
+  }
+}
+
 // db_creator.cpp:167-241 on the device: key of every indexable position (or 0xFFFFFFFF).
 __global__ void index_keys_kernel(const uint8_t *seq, uint32_t seq_len, const uint32_t *seq_starts,
                                   uint32_t n_seqs, uint32_t seed, uint32_t seed_len, uint32_t *keys,
@@ -173,6 +196,7 @@ struct DbChunk {
   DevBuf<uint32_t> keys_count, positions, seq_starts;
   uint32_t seq_len = 0, keys_count_len = 0, positions_len = 0, n_seqs = 0;
   bool valid = false;
+  bool has_index = false;   // false: sequence-only chunk (gm_db_upload_seq), Merge/TraceBack side
 };
 
 }  // namespace
@@ -208,6 +232,7 @@ struct gm_context {
   DevBuf<uint32_t> staging;
   uint32_t staging_cap = 1u << 15;
   DevBuf<uint32_t> prefix;            // scan output (n_queries + 1)
+  DevBuf<uint32_t> bounds;            // gm_candidates_pack part boundaries
   DevBuf<uint32_t> gather0, gather1, gather2;
   DevBuf<uint32_t> strip_scratch;
   DevBuf<unsigned long long> counters;  // [0] cand cursor [1] positions visited [2] cells [3] big cursor
@@ -326,7 +351,7 @@ extern "C" void gm_destroy(gm_context *c) {
   c->matrix.release(); c->queries.release(); c->run_first.release(); c->run_last.release();
   c->cand_off.release(); c->cand_cnt.release(); c->cand_start.release(); c->cand_score.release();
   c->cand_end.release(); c->staging.release(); c->prefix.release(); c->gather0.release();
-  c->gather1.release(); c->gather2.release(); c->strip_scratch.release(); c->counters.release();
+  c->gather1.release(); c->gather2.release(); c->bounds.release(); c->strip_scratch.release(); c->counters.release();
   c->small.release(); c->hits[0].release(); c->hits[1].release(); c->hit_cnt[0].release();
   c->hit_cnt[1].release(); c->jobs.release(); c->big_scratch.release(); c->tb_work.release(); c->chunk_tab.release();
   for (auto &e : c->ev) cudaEventDestroy(e);
@@ -400,6 +425,33 @@ extern "C" int gm_db_upload(gm_context *c, uint32_t id, const uint8_t *seq, uint
   ch.positions_len = positions_len;
   ch.n_seqs = n_seqs;
   ch.valid = true;
+  ch.has_index = true;
+  c->chunk_tab_dirty = true;
+  if (c->cur_chunk == (int)id) c->cur_chunk = -1;
+  return 0;
+}
+
+extern "C" int gm_db_upload_seq(gm_context *c, uint32_t id, const uint8_t *seq, uint32_t seq_len,
+                                const uint32_t *seq_starts, uint32_t n_seqs) {
+  if (int r = check_ctx(c)) return r;
+  if (id >= GM_MAX_DB_CHUNKS) return fail(GM_ERR_ARGUMENT, "chunk id %u out of range", id);
+  if (!seq || !seq_starts || n_seqs == 0) return fail(GM_ERR_ARGUMENT, "null db arrays");
+  DbChunk &ch = c->chunks[id];
+  ch.valid = false;
+  ch.keys_count.release();
+  ch.positions.release();
+  GM_CUDA(ch.seq.ensure(seq_len));
+  GM_CUDA(ch.seq_starts.ensure(n_seqs));
+  GM_CUDA(cudaMemcpyAsync(ch.seq.p, seq, seq_len, cudaMemcpyHostToDevice, c->stream));
+  GM_CUDA(cudaMemcpyAsync(ch.seq_starts.p, seq_starts, (size_t)n_seqs * 4, cudaMemcpyHostToDevice,
+                          c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  ch.seq_len = seq_len;
+  ch.keys_count_len = 0;
+  ch.positions_len = 0;
+  ch.n_seqs = n_seqs;
+  ch.valid = true;
+  ch.has_index = false;
   c->chunk_tab_dirty = true;
   if (c->cur_chunk == (int)id) c->cur_chunk = -1;
   return 0;
@@ -466,6 +518,8 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
   if (id >= GM_MAX_DB_CHUNKS || !c->chunks[id].valid)
     return fail(GM_ERR_ARGUMENT, "db chunk %u is not resident", id);
   DbChunk &ch = c->chunks[id];
+  if (!ch.has_index)
+    return fail(GM_ERR_ARGUMENT, "db chunk %u is sequence-only (gm_db_upload_seq): no index to search", id);
   GM_CUDA(c->cand_start.ensure(c->cand_capacity));
   const int grid = c->sm_count;
   GM_CUDA(c->staging.ensure((size_t)grid * 2 * c->staging_cap));  // the fast kernel runs 2 CTAs per SM
@@ -601,6 +655,83 @@ extern "C" int gm_candidates_download(gm_context *c, uint32_t first, uint32_t en
   if (starts) GM_CUDA(cudaMemcpyAsync(starts, c->gather0.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
   if (query_ids) GM_CUDA(cudaMemcpyAsync(query_ids, c->gather2.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
   GM_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gm_candidates_pack(gm_context *c, uint32_t n_parts, const uint32_t *bounds,
+                                  uint32_t *counts_dev, uint32_t *data_dev,
+                                  uint64_t data_capacity_words, uint64_t *part_totals) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  if (c->cur_chunk < 0) return fail(GM_ERR_ARGUMENT, "no searched db chunk (gm_search)");
+  if (n_parts == 0 || !bounds || bounds[0] != 0 || bounds[n_parts] != c->n_queries)
+    return fail(GM_ERR_ARGUMENT, "bounds must run from 0 to n_queries");
+  uint64_t total = 0;
+  for (uint32_t p = 0; p < n_parts; ++p) {
+    if (bounds[p] > bounds[p + 1]) return fail(GM_ERR_ARGUMENT, "bounds must ascend");
+    uint64_t m = 0;
+    for (uint32_t q = bounds[p]; q < bounds[p + 1]; ++q) m += c->h_counts[q];
+    if (part_totals) part_totals[p] = m;
+    total += m;
+  }
+  if (counts_dev)
+    GM_CUDA(cudaMemcpyAsync(counts_dev, c->cand_cnt.p, (size_t)c->n_queries * 4,
+                            cudaMemcpyDeviceToDevice, c->stream));
+  if (data_dev && total) {
+    if (3 * total > data_capacity_words)
+      return fail(GM_ERR_CAPACITY, "pack buffer holds %llu words, %llu needed",
+                  (unsigned long long)data_capacity_words, (unsigned long long)(3 * total));
+    if (!c->cand_score.p || !c->cand_end.p) return fail(GM_ERR_ARGUMENT, "candidates are not scored (gm_score)");
+    if (int r = scan_counts(c, 0, c->n_queries, 0, nullptr)) return r;
+    GM_CUDA(c->bounds.ensure(n_parts + 1));
+    GM_CUDA(cudaMemcpyAsync(c->bounds.p, bounds, (size_t)(n_parts + 1) * 4, cudaMemcpyHostToDevice,
+                            c->stream));
+    pack_kernel<<<c->sm_count * 8, 128, 0, c->stream>>>(c->cand_off.p, c->cand_cnt.p, c->prefix.p,
+                                                        c->n_queries, c->bounds.p, n_parts,
+                                                        c->cand_start.p, c->cand_score.p,
+                                                        c->cand_end.p, data_dev);
+    GM_CUDA(cudaGetLastError());
+  }
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gm_candidates_import(gm_context *c, uint32_t id, const uint32_t *counts_dev,
+                                    const uint32_t *data_dev, uint64_t total) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  if (id >= GM_MAX_DB_CHUNKS || !c->chunks[id].valid)
+    return fail(GM_ERR_ARGUMENT, "db chunk %u is not resident", id);
+  if (!counts_dev || (!data_dev && total)) return fail(GM_ERR_ARGUMENT, "null candidate buffers");
+  if (total > c->cand_capacity)
+    return fail(GM_ERR_CAPACITY, "candidate buffer (%llu entries) too small for %llu imported; raise "
+                "it with gm_set_candidate_capacity", (unsigned long long)c->cand_capacity,
+                (unsigned long long)total);
+  c->cur_chunk = -1;
+  GM_CUDA(c->cand_start.ensure(c->cand_capacity));
+  GM_CUDA(c->cand_score.ensure(c->cand_capacity));
+  GM_CUDA(c->cand_end.ensure(c->cand_capacity));
+  c->h_counts.assign(c->n_queries, 0);
+  GM_CUDA(cudaMemcpyAsync(c->cand_cnt.p, counts_dev, (size_t)c->n_queries * 4,
+                          cudaMemcpyDeviceToDevice, c->stream));
+  GM_CUDA(cudaMemcpyAsync(c->h_counts.data(), counts_dev, (size_t)c->n_queries * 4,
+                          cudaMemcpyDeviceToHost, c->stream));
+  if (int r = scan_counts(c, 0, c->n_queries, 0, nullptr)) return r;
+  GM_CUDA(cudaMemcpyAsync(c->cand_off.p, c->prefix.p, (size_t)c->n_queries * 4,
+                          cudaMemcpyDeviceToDevice, c->stream));
+  if (total) {
+    GM_CUDA(cudaMemcpyAsync(c->cand_start.p, data_dev, total * 4, cudaMemcpyDeviceToDevice, c->stream));
+    GM_CUDA(cudaMemcpyAsync(c->cand_score.p, data_dev + total, total * 4, cudaMemcpyDeviceToDevice, c->stream));
+    GM_CUDA(cudaMemcpyAsync(c->cand_end.p, data_dev + 2 * total, total * 4, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  uint64_t sum = 0;
+  for (uint32_t v : c->h_counts) sum += v;
+  if (sum != total)
+    return fail(GM_ERR_ARGUMENT, "imported counts add up to %llu, not %llu", (unsigned long long)sum,
+                (unsigned long long)total);
+  c->cand_total = sum;
+  c->cur_chunk = (int)id;
   return 0;
 }
 
@@ -1014,6 +1145,7 @@ extern "C" int gm_db_build_index(gm_context *c, uint32_t id, const uint8_t *seq,
   ch.keys_count_len = n_keys + 1;
   ch.positions_len = n_pos;
   ch.valid = true;
+  ch.has_index = true;
   c->chunk_tab_dirty = true;
   if (c->cur_chunk == (int)id) c->cur_chunk = -1;
   return 0;

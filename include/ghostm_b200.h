@@ -223,6 +223,32 @@ int gm_score(gm_context *ctx, uint32_t first_query, uint32_t end_query, uint32_t
 /* Merge + TraceBack of the scored candidates of [first_query, end_query) into the hit lists. */
 int gm_merge(gm_context *ctx, uint32_t first_query, uint32_t end_query, gm_stats *stats);
 
+/* ---- db-sharded runs: front (search + SW, one db chunk per GPU) / back (Merge + TraceBack of
+ * one query slice per GPU) with one exchange of scored candidates between them.  The reference
+ * has no counterpart (single GPU); what is preserved is its Merge order: every query slice sees
+ * the db chunks in ascending order with exactly the candidates Aligner::Execute would hand to
+ * Merge (aligner.cpp:131-171). ---- */
+
+/* Sequence-only db chunk for the back side: residues + .pos table (DB::GetID, TraceBack
+ * windows), no index.  gm_search on such a chunk fails with GM_ERR_ARGUMENT. */
+int gm_db_upload_seq(gm_context *ctx, uint32_t chunk_id, const uint8_t *seq, uint32_t seq_len,
+                     const uint32_t *seq_starts, uint32_t n_seqs);
+/* Pack the scored candidates of the searched chunk by query slice.  bounds[n_parts + 1] are
+ * ascending query indices (bounds[0] = 0, bounds[n_parts] = n_queries).  DEVICE outputs:
+ * counts_dev[n_queries] = per-query candidate counts; data_dev = for every part p a block
+ * [start[m_p] | score[m_p] | end[m_p]] in reference order (query, then region, ascending),
+ * blocks in part order, 3 * sum(m_p) words in total (data_capacity_words is checked).
+ * HOST output: part_totals[n_parts] = m_p.  data_dev may be NULL (totals only). */
+int gm_candidates_pack(gm_context *ctx, uint32_t n_parts, const uint32_t *bounds,
+                       uint32_t *counts_dev, uint32_t *data_dev, uint64_t data_capacity_words,
+                       uint64_t *part_totals);
+/* Install scored candidates of db chunk chunk_id (resident, possibly sequence-only) for ALL
+ * resident queries from DEVICE buffers laid out like one gm_candidates_pack part: counts_dev
+ * [n_queries] and data_dev = [start[total] | score[total] | end[total]].  Afterwards gm_merge
+ * behaves as after gm_search + gm_score on that chunk. */
+int gm_candidates_import(gm_context *ctx, uint32_t chunk_id, const uint32_t *counts_dev,
+                         const uint32_t *data_dev, uint64_t total);
+
 /* Device-side synthetic data and index construction (bench only; db_creator.cpp:167-241). */
 int gm_db_build_index(gm_context *ctx, uint32_t chunk_id, const uint8_t *seq, uint32_t seq_len,
                       const uint32_t *seq_starts, uint32_t n_seqs, uint32_t seed);

@@ -60,3 +60,96 @@ def test_hit_lists(gpu_ctx, name, deferred, fast):
     assert int(ref.counts.sum()) > 0
     gpu_ctx.set_deferred_traceback(True)
     gpu_ctx.set_search_variant(True)
+
+
+@pytest.mark.parametrize("name,world", [("small", 3), ("repeats", 2), ("options", 2), ("frames6", 4),
+                                        ("long", 2)])
+def test_shard_front_back_on_one_gpu(name, world):
+    """ghostm_b200.shard with `world` simulated ranks on one device: chunk-parallel front
+    (search + SW + gm_candidates_pack), exchange by query slice, query-sliced back
+    (gm_candidates_import + Merge + TraceBack on sequence-only chunks).  Every slice must hold
+    exactly the oracle's single-process hit lists."""
+    from ghostm_b200 import capi, shard
+    db, qchunks, kw = H.workload(name)
+    opt = O.Options(**kw)
+    front_ctx = capi.Context(0)
+    H.setup_context(front_ctx, db, opt)
+    n_chunks = len(db.chunks)
+    total_hits = 0
+    for qc in qchunks:
+        ref = O.align_chunk(qc, db, opt)
+        bounds = shard.slice_bounds(qc.name_breaks(), qc.n, world)
+        front_ctx.query_upload(qc.seqs, qc.name_breaks())
+        fronts = [shard.GpuFront(front_ctx, qc.n, 1 << 22, "cuda:0") for _ in range(world)]
+        backs = []
+        for r in range(world):
+            base, stop = int(bounds[r]), int(bounds[r + 1])
+            if stop == base:
+                backs.append(None)
+                continue
+            ctx = capi.Context(0)
+            ctx.set_options(db.seed, opt.matrix, shift=opt.shift, log_region=opt.log_region,
+                            threshold=opt.threshold, extend=opt.extend, best=opt.best,
+                            max_list_length=opt.max_list_length, open_gap=opt.open_gap,
+                            extend_gap=opt.extend_gap)
+            ctx.set_candidate_capacity(1 << 22)
+            for i, ch in enumerate(db.chunks):
+                ctx.db_upload_seq(i, ch.seq, ch.seq_starts)
+            sl = H.slice_query_chunk(qc, base, stop)
+            ctx.query_upload(sl.seqs, sl.name_breaks())
+            backs.append(shard.GpuBack(ctx))
+        for round0 in range(0, n_chunks, world):
+            outboxes = [shard.front_round(fronts[r], round0 + r, n_chunks, bounds) for r in range(world)]
+            inboxes = shard.exchange_local(outboxes, bounds)
+            for r in range(world):
+                if backs[r] is not None:
+                    shard.back_round(backs[r], inboxes[r], round0, n_chunks, int(bounds[r]),
+                                     int(bounds[r + 1]))
+        for r in range(world):
+            if backs[r] is None:
+                continue
+            base, stop = int(bounds[r]), int(bounds[r + 1])
+            backs[r].finish()
+            hits, counts = backs[r].ctx.results()
+            assert np.array_equal(counts, ref.counts[base:stop])
+            for i in range(base, stop):
+                got = hits[i - base, :counts[i - base]].copy()
+                got["query_id"] += base
+                ok, field = H.hits_equal(got, ref.hits[i, :ref.counts[i]])
+                assert ok, (name, r, i, field)
+            total_hits += int(counts.sum())
+            backs[r].ctx.close()
+    front_ctx.close()
+    assert total_hits > 0
+
+
+def test_sequence_only_chunk_refuses_search(gpu_ctx):
+    from ghostm_b200 import capi
+    db, qchunks, kw = H.workload("small")
+    opt = O.Options(**kw)
+    H.setup_context(gpu_ctx, db, opt)
+    gpu_ctx.db_upload_seq(0, db.chunks[0].seq, db.chunks[0].seq_starts)
+    gpu_ctx.query_upload(qchunks[0].seqs, qchunks[0].name_breaks())
+    with pytest.raises(capi.GhostmError, match="sequence-only"):
+        gpu_ctx.search(0)
+    gpu_ctx.db_upload(0, db.chunks[0])
+
+
+def test_shard_over_nccl_all_visible_gpus(tmp_path):
+    """The same front/back split with one process per GPU and the exchange over NCCL
+    (tools/shard_check.py); needs at least two visible GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    n = min(n, 4)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port",
+                          "29621", os.path.join(root, "tools", "shard_check.py"), "small", "repeats"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert out.stdout.count("SHARD_GPU_OK") == 2 * n

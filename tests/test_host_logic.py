@@ -190,3 +190,101 @@ def test_ring_over_gloo_world2(tmp_path):
                           str(script)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "RING_OK" in out.stdout
+
+
+# ---- ghostm_b200.shard: chunk-parallel front, query-sliced back ------------------------------
+
+from ghostm_b200 import shard
+
+
+def test_slice_bounds_respect_runs():
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 100, 1001):
+        for world in (1, 2, 3, 8):
+            nb = (rng.random(n) < 0.4).astype(np.uint8)
+            b = shard.slice_bounds(nb, n, world)
+            assert b[0] == 0 and b[-1] == n and np.all(np.diff(b.astype(np.int64)) >= 0)
+            for x in b[1:-1]:
+                assert x == n or x == 0 or nb[x], (n, world, b)
+            b2 = shard.slice_bounds(None, n, world)
+            assert b2[0] == 0 and b2[-1] == n
+            assert np.diff(b2.astype(np.int64)).max() - np.diff(b2.astype(np.int64)).min() <= 1
+
+
+def _assert_slices_equal_single(qc, db, opt, backs, bounds):
+    single = O.align_chunk(qc, db, opt)
+    for r, back in enumerate(backs):
+        base, stop = int(bounds[r]), int(bounds[r + 1])
+        assert np.array_equal(single.counts[base:stop], back.res.counts)
+        for i in range(base, stop):
+            a = single.hits[i, :single.counts[i]].copy()
+            b = back.res.hits[i - base, :single.counts[i]].copy()
+            b["query_id"] += base
+            assert a.tobytes() == b.tobytes(), (r, i)
+    return int(single.counts.sum())
+
+
+@pytest.mark.parametrize("name,world", [("small", 3), ("repeats", 2), ("options", 4), ("frames6", 2)])
+def test_shard_local_simulation_matches_single(name, world):
+    """All ranks simulated in one process with the oracle as engine: every query slice must end
+    with exactly the single-process hit lists (several db chunks, same-name runs, candidate-chunk
+    cuts, best > 16 where Merge re-sorts the carried lists on every call)."""
+    db, qchunks, kw = H.workload(name)
+    opt = O.Options(**kw)
+    qc = qchunks[0]
+    bounds = shard.slice_bounds(qc.name_breaks(), qc.n, world)
+    fronts = [H.OracleFront(qc, db, opt) for _ in range(world)]
+    backs = [H.OracleBack(H.slice_query_chunk(qc, int(bounds[r]), int(bounds[r + 1])), db, opt)
+             for r in range(world)]
+    n_chunks = len(db.chunks)
+    for round0 in range(0, n_chunks, world):
+        outboxes = [shard.front_round(fronts[r], round0 + r, n_chunks, bounds) for r in range(world)]
+        inboxes = shard.exchange_local(outboxes, bounds)
+        for r in range(world):
+            shard.back_round(backs[r], inboxes[r], round0, n_chunks, int(bounds[r]), int(bounds[r + 1]))
+    assert _assert_slices_equal_single(qc, db, opt, backs, bounds) > 0
+
+
+_SHARD_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from ghostm_b200 import shard
+from oracle import oracle as O
+from tests import helpers as H
+from tests.test_host_logic import _assert_slices_equal_single
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+db, qchunks, kw = H.workload("small")
+opt = O.Options(**kw)
+qc = qchunks[0]
+bounds = shard.slice_bounds(qc.name_breaks(), qc.n, world)
+front = H.OracleFront(qc, db, opt)
+back = H.OracleBack(H.slice_query_chunk(qc, int(bounds[rank]), int(bounds[rank + 1])), db, opt)
+shard.shard_step(front, back, dist, rank, world, len(db.chunks), bounds)
+backs = [back if r == rank else None for r in range(world)]
+single = O.align_chunk(qc, db, opt)
+base, stop = int(bounds[rank]), int(bounds[rank + 1])
+assert np.array_equal(single.counts[base:stop], back.res.counts)
+for i in range(base, stop):
+    a = single.hits[i, :single.counts[i]].copy()
+    b = back.res.hits[i - base, :single.counts[i]].copy()
+    b["query_id"] += base
+    assert a.tobytes() == b.tobytes(), (rank, i)
+print("SHARD_OK", rank, int(back.res.counts.sum()))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_shard_over_gloo_world2(tmp_path):
+    """db chunks sharded over 2 ranks, candidates exchanged by query slice over gloo all-to-all:
+    each rank must hold exactly the single-process lists of its slice."""
+    script = tmp_path / "w.py"
+    script.write_text(_SHARD_WORKER.format(root=ROOT))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29613",
+                          str(script)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert out.stdout.count("SHARD_OK") == 2
