@@ -908,7 +908,7 @@ extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *s
   const int src = c->cur_hits, dst = src ^ 1;
   uint64_t n_new = 0;
   for (uint32_t q = first; q < end; ++q) n_new += c->h_counts[q];
-  const uint64_t big_cap = n_new + (uint64_t)c->n_queries * c->cap + 1;
+  const uint64_t big_cap = 2 * (n_new + (uint64_t)c->n_queries * c->cap) + 2;  // records + stopper positions
   GM_CUDA(c->big_scratch.ensure(big_cap));
   MergeParams p = {};
   p.queries = c->queries.p;

@@ -125,9 +125,10 @@ __device__ void insertion_sort_(Rec *first, Rec *last) {
   }
 }
 
-// std::sort(first, first + n, comp), replayed LAZILY.  Only a prefix of the sorted array is ever
-// read by the Merge walk (it stops after `best` accepted hits), and the prefix can be produced
-// without touching most of the array, move for move identical to the full sort:
+// std::sort(first, first + n, comp), replayed LAZILY and WARP-COOPERATIVELY.  Only a prefix of
+// the sorted array is ever read by the Merge walk (it stops after `best` accepted hits), and the
+// prefix can be produced without touching most of the array, move for move identical to the
+// full sort:
 //  * __introsort_loop recurses into [cut, last) and loops on [first, cut); the two halves are
 //    disjoint and never exchange elements afterwards, so the right halves can wait on a stack
 //    until the walk actually needs positions inside them;
@@ -135,106 +136,150 @@ __device__ void insertion_sort_(Rec *first, Rec *last) {
 //    ranges), each block >= the next one under the comparator; __final_insertion_sort inserts
 //    elements left to right and an element never crosses into an earlier block (the comparison
 //    is strict), so positions [0, e) are final as soon as every element before the block
-//    boundary e has been inserted.
-template <typename Rec>
-struct LazySort {
-  struct Frame { long first, last; int depth; };
+//    boundary e has been inserted;
+//  * __unguarded_partition(f+1, l, pivot = *f) is a fixed function of the array, not of the
+//    order in which a machine evaluates it: with L_1 < L_2 < ... the positions whose key is
+//    <= the pivot's ("left stoppers") and R_1 > R_2 > ... those whose key is >= it ("right
+//    stoppers"), the scan pointers only ever rest on untouched positions or on the partner of
+//    the previous swap, hence the sequential loop performs exactly the swaps L_k <-> R_k for
+//    k = 1..K, K = #{k : L_k < R_k} (monotone), and returns L_1 if K = 0, else
+//    min(L_{K+1}, R_K).  The warp compacts both stopper lists with ballots, finds K and does
+//    the K swaps in parallel (checked against the sequential loop in
+//    tests/test_host_logic.py::test_parallel_partition_identity).
+// All lanes run the same control flow on replicated scalars; lane 0 alone executes the short
+// sequential pieces (median of three, insertion of <= 16-element blocks, heapsort fallback).
+template <typename Rec, typename Pos>
+struct WarpLazySort {
+  struct Frame { int first, last, depth; };
   Rec *a;
-  long n;
-  long looped;     // [0, looped) went through the introsort loop phase (block boundary)
-  long final_end;  // [0, final_end) is in its final sorted place
+  Pos *lpos, *rasc;   // scratch: left stoppers ascending, right stoppers ascending (n entries each)
+  int n;
+  int looped;     // [0, looped) went through the introsort loop phase (block boundary)
+  int final_end;  // [0, final_end) is in its final sorted place
   int sp;
   Frame stack[64];
 
-  __device__ void init(Rec *arr, long count) {
+  __device__ void init(Rec *arr, Pos *scratch, int count) {
     a = arr;
+    lpos = scratch;
+    rasc = scratch + count;
     n = count;
     looped = 0;
     final_end = 0;
     sp = 0;
     int lg = 0;
-    for (long m = count; m > 1; m >>= 1) ++lg;
+    for (int m = count; m > 1; m >>= 1) ++lg;
     if (count > 0) stack[sp++] = Frame{0, count, lg * 2};
   }
 
-  __device__ void loop_next_block() {  // __introsort_loop on the leftmost pending range
-    Frame fr = stack[--sp];
-    Rec *f = a + fr.first, *l = a + fr.last;
-    int depth = fr.depth;
+  __device__ void loop_next_block(uint32_t lane) {  // __introsort_loop on the leftmost pending range
+    const Frame fr = stack[--sp];
+    int f = fr.first, l = fr.last, depth = fr.depth;
     while (l - f > 16) {
       if (depth == 0) {
-        heap_sort_(f, l);
+        if (lane == 0) heap_sort_(a + f, a + l);
+        __syncwarp();
         break;
       }
       --depth;
-      Rec *mid = f + (l - f) / 2;
-      Rec *x = f + 1, *y = mid, *z = l - 1;    // __move_median_to_first(f, x, y, z)
-      if (comp(*x, *y)) {
-        if (comp(*y, *z)) swap_(f, y);
-        else if (comp(*x, *z)) swap_(f, z);
-        else swap_(f, x);
-      } else if (comp(*x, *z)) swap_(f, x);
-      else if (comp(*y, *z)) swap_(f, z);
-      else swap_(f, y);
-      Rec *lo = f + 1, *hi = l;                // __unguarded_partition(f + 1, l, f)
-      const Rec pivot = *f;
-      while (true) {
-        while (comp(*lo, pivot)) ++lo;
-        --hi;
-        while (comp(pivot, *hi)) --hi;
-        if (!(lo < hi)) break;
-        swap_(lo, hi);
-        ++lo;
+      if (lane == 0) {
+        Rec *pf = a + f, *x = pf + 1, *y = pf + (l - f) / 2, *z = a + l - 1;  // __move_median_to_first
+        if (comp(*x, *y)) {
+          if (comp(*y, *z)) swap_(pf, y);
+          else if (comp(*x, *z)) swap_(pf, z);
+          else swap_(pf, x);
+        } else if (comp(*x, *z)) swap_(pf, x);
+        else if (comp(*y, *z)) swap_(pf, z);
+        else swap_(pf, y);
       }
-      stack[sp++] = Frame{(long)(lo - a), (long)(l - a), depth};
-      l = lo;
+      __syncwarp();
+      const uint32_t pk = RecKey<Rec>::key(a[f]);
+      const uint32_t lt = (1u << lane) - 1u;
+      uint32_t nA = 0, nB = 0;
+      for (int base = f + 1; base < l; base += 32) {     // __unguarded_partition(f + 1, l, f)
+        const int i = base + (int)lane;
+        const bool valid = i < l;
+        const uint32_t k = valid ? RecKey<Rec>::key(a[i]) : 0u;
+        const bool isA = valid && k <= pk, isB = valid && k >= pk;
+        const uint32_t ba = __ballot_sync(kFull, isA), bb = __ballot_sync(kFull, isB);
+        if (isA) lpos[nA + __popc(ba & lt)] = (Pos)i;
+        if (isB) rasc[nB + __popc(bb & lt)] = (Pos)i;
+        nA += __popc(ba);
+        nB += __popc(bb);
+      }
+      __syncwarp();
+      const uint32_t mn = nA < nB ? nA : nB;
+      uint32_t K = 0;
+      for (uint32_t k0 = 0; k0 < mn; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool ok = k < mn && (uint32_t)lpos[k] < (uint32_t)rasc[nB - 1 - k];
+        const uint32_t b = __ballot_sync(kFull, ok);
+        K += __popc(b);
+        if (b != kFull) break;
+      }
+      for (uint32_t k = lane; k < K; k += 32) swap_(a + lpos[k], a + rasc[nB - 1 - k]);
+      int cut;
+      if (K == 0) {
+        cut = (int)lpos[0];
+      } else {
+        const int c2 = (int)rasc[nB - K];
+        cut = (K < nA && (int)lpos[K] < c2) ? (int)lpos[K] : c2;
+      }
+      __syncwarp();
+      stack[sp++] = Frame{cut, l, depth};
+      l = cut;
     }
-    looped = l - a;
+    looped = l;
   }
 
   // make position i final; returns false if i >= n
-  __device__ bool ensure(long i) {
+  __device__ bool ensure(int i, uint32_t lane) {
     if (i >= n) return false;
     while (final_end <= i) {
-      if (looped == final_end) loop_next_block();
-      for (long k = final_end; k < looped; ++k) {   // __final_insertion_sort, element k
-        if (k == 0) continue;
-        Rec *e = a + k;
-        if ((n <= 16 || k < 16) && comp(*e, *a)) {  // __insertion_sort's guarded branch
-          const Rec val = *e;
-          for (Rec *q = e; q != a; --q) *q = *(q - 1);
-          *a = val;
-        } else {
-          unguarded_linear_insert_(e);
+      if (looped == final_end) loop_next_block(lane);
+      if (lane == 0) {
+        for (int k = final_end; k < looped; ++k) {   // __final_insertion_sort, element k
+          if (k == 0) continue;
+          Rec *e = a + k;
+          if ((n <= 16 || k < 16) && comp(*e, *a)) {  // __insertion_sort's guarded branch
+            const Rec val = *e;
+            for (Rec *q = e; q != a; --q) *q = *(q - 1);
+            *a = val;
+          } else {
+            unguarded_linear_insert_(e);
+          }
         }
       }
+      __syncwarp();
       final_end = looped;
     }
     return true;
   }
 };
 
-// DB::GetID, db.h:94-120
-__device__ uint32_t db_get_id(const uint32_t *pos, uint32_t n_seqs, uint32_t seq_len, uint32_t position) {
-  if (pos[n_seqs - 1] <= position && position < seq_len) return n_seqs - 1;
-  if (n_seqs < 2) return kNoId;
-  uint32_t left = 0, right = n_seqs - 2;
-  while (left <= right) {
-    const uint32_t mid = (left + right) / 2;
-    if (pos[mid] <= position && position < pos[mid + 1]) return mid;
-    if (pos[mid] < position) {
-      left = mid + 1;
-    } else {
-      if (mid == 0) break;
-      right = mid - 1;
-    }
+// DB::GetID, db.h:94-120: the id with pos[id] <= position < pos[id + 1] (the last sequence ends
+// at seq_len); the reference's binary search returns UINT_MAX when there is none.  Same answer
+// from a warp-wide 32-ary search (4 rounds instead of 19 dependent loads for 350 k sequences).
+__device__ uint32_t db_get_id(const uint32_t *pos, uint32_t n_seqs, uint32_t seq_len,
+                              uint32_t position, uint32_t lane) {
+  if (position >= seq_len || pos[0] > position) return kNoId;
+  if (pos[n_seqs - 1] <= position) return n_seqs - 1;
+  uint32_t lo = 0, hi = n_seqs - 1;       // answer in [lo, hi), pos[lo] <= position < pos[hi]
+  while (hi - lo > 1) {
+    const uint32_t step = (hi - lo + 31) / 32;
+    const uint32_t idx = lo + lane * step;
+    const bool ok = idx < hi && pos[idx] <= position;
+    const uint32_t b = __ballot_sync(kFull, ok);
+    const uint32_t nlo = lo + (31 - __clz(b)) * step;
+    hi = hi < nlo + step ? hi : nlo + step;
+    lo = nlo;
   }
-  return kNoId;
+  return lo;
 }
 
-template <typename Rec>
-__device__ void merge_run(const MergeParams &p, Rec *list, uint32_t n_new, uint32_t n_old,
-                          uint32_t qf, uint32_t ql, uint32_t lane) {
+template <typename Rec, typename Pos>
+__device__ void merge_run(const MergeParams &p, Rec *list, Pos *scratch, uint32_t n_new,
+                          uint32_t n_old, uint32_t qf, uint32_t ql, uint32_t lane) {
   constexpr bool kWide = sizeof(Rec) == 8;
   const uint32_t n = n_new + n_old;
   // ---- build the list in reference order (aligner.cpp:732-740)
@@ -255,66 +300,71 @@ __device__ void merge_run(const MergeParams &p, Rec *list, uint32_t n_new, uint3
     else list[n_new + i] = (Rec)((score << 16) | kCarriedFlag | i);
   }
   __syncwarp();
-  if (lane == 0) {
-    LazySort<Rec> sorter;
-    sorter.init(list, (long)n);
-    // ---- walk (aligner.cpp:703-725 / :746-768) over the lazily sorted list
-    uint32_t out = 0;
-    gm_hit *dst = p.new_hits + (size_t)ql * p.cap;
-    for (uint32_t it = 0; it < n; ++it) {
-      sorter.ensure((long)it);
-      const Rec r = list[it];
-      const uint32_t ref = kWide ? (uint32_t)r : ((uint32_t)r & 0xFFFFu);
-      const bool carried = kWide ? (ref & 0x80000000u) != 0 : (ref & kCarriedFlag) != 0;
-      if (carried) {
-        const uint32_t idx = kWide ? (ref & 0x7FFFFFFFu) : (ref & 0x7FFFu);
-        if (out < p.cap) dst[out] = p.old_hits[(size_t)ql * p.cap + idx];
-        ++out;
-      } else {
-        // locate (query, i) of list position ref
-        uint32_t q = qf, rem = ref;
-        for (;; ++q) {
-          if (q < p.first_query || q >= p.end_query) continue;
-          const uint32_t cnt = p.cand_cnt[q];
-          if (rem < cnt) break;
-          rem -= cnt;
-        }
-        const uint32_t g = p.cand_off[q] + rem;
-        const uint32_t end = p.cand_end[g];
-        const uint32_t db_id = db_get_id(p.seq_starts, p.n_seqs, p.db_len, end);
-        bool seen = false;  // overlap[db_id] == id (aligner.cpp:707): accepted earlier in this call
-        for (uint32_t k = 0; k < out && k < p.cap; ++k)
-          seen |= dst[k].db_chunk == p.db_chunk && dst[k].db_id == db_id &&
-                  dst[k].aln_match == kNoId && dst[k].aln_len == p.serial;
-        if (!seen) {
-          if (out < p.cap) {
-            gm_hit h;
-            h.query_id = q;
-            h.db_id = db_id;
-            h.db_chunk = p.db_chunk;
-            h.score = p.cand_score[g];
-            h.db_start = p.cand_start[g];
-            h.db_end = end;          // absolute; TraceBack makes both sequence-relative
-            h.aln_len = p.serial;    // accepted by this call ...
-            h.aln_match = kNoId;     // ... TraceBack pending
-            h.seq_id = 0.f;
-            dst[out] = h;
-            if (!p.deferred) p.jobs[atomicAdd(p.n_jobs, 1u)] = ql * p.cap + out;
-          }
-          ++out;
-        }
+  WarpLazySort<Rec, Pos> sorter;
+  sorter.init(list, scratch, (int)n);
+  // ---- walk (aligner.cpp:703-725 / :746-768) over the lazily sorted list, warp-uniform
+  uint32_t out = 0;
+  gm_hit *dst = p.new_hits + (size_t)ql * p.cap;
+  const gm_hit *old = p.old_hits + (size_t)ql * p.cap;
+  for (uint32_t it = 0; it < n; ++it) {
+    sorter.ensure((int)it, lane);
+    const Rec r = list[it];
+    const uint32_t ref = kWide ? (uint32_t)r : ((uint32_t)r & 0xFFFFu);
+    const bool carried = kWide ? (ref & 0x80000000u) != 0 : (ref & kCarriedFlag) != 0;
+    if (carried) {
+      const uint32_t idx = kWide ? (ref & 0x7FFFFFFFu) : (ref & 0x7FFFu);
+      if (out < p.cap && lane < sizeof(gm_hit) / 4)
+        reinterpret_cast<uint32_t *>(dst + out)[lane] = reinterpret_cast<const uint32_t *>(old + idx)[lane];
+      ++out;
+    } else {
+      // locate (query, i) of list position ref
+      uint32_t q = qf, rem = ref;
+      for (;; ++q) {
+        if (q < p.first_query || q >= p.end_query) continue;
+        const uint32_t cnt = p.cand_cnt[q];
+        if (rem < cnt) break;
+        rem -= cnt;
       }
-      if (out >= p.best) break;  // aligner.cpp:722-724
+      const uint32_t g = p.cand_off[q] + rem;
+      const uint32_t end = p.cand_end[g];
+      const uint32_t db_id = db_get_id(p.seq_starts, p.n_seqs, p.db_len, end, lane);
+      // overlap[db_id] == id (aligner.cpp:707): accepted earlier in this call
+      const uint32_t have = out < p.cap ? out : p.cap;
+      bool mine = false;
+      for (uint32_t k = lane; k < have; k += 32)
+        mine |= dst[k].db_chunk == p.db_chunk && dst[k].db_id == db_id &&
+                dst[k].aln_match == kNoId && dst[k].aln_len == p.serial;
+      if (!__any_sync(kFull, mine)) {
+        if (out < p.cap && lane == 0) {
+          gm_hit h;
+          h.query_id = q;
+          h.db_id = db_id;
+          h.db_chunk = p.db_chunk;
+          h.score = p.cand_score[g];
+          h.db_start = p.cand_start[g];
+          h.db_end = end;          // absolute; TraceBack makes both sequence-relative
+          h.aln_len = p.serial;    // accepted by this call ...
+          h.aln_match = kNoId;     // ... TraceBack pending
+          h.seq_id = 0.f;
+          dst[out] = h;
+          if (!p.deferred) p.jobs[atomicAdd(p.n_jobs, 1u)] = ql * p.cap + out;
+        }
+        ++out;
+      }
     }
-    p.new_cnt[ql] = out < p.cap ? out : p.cap;
+    __syncwarp();
+    if (out >= p.best) break;  // aligner.cpp:722-724
   }
+  if (lane == 0) p.new_cnt[ql] = out < p.cap ? out : p.cap;
   __syncwarp();
 }
 
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams p) {
   extern __shared__ __align__(16) uint32_t lists[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t *my_list = lists + (size_t)warp * p.smem_elems;
+  // per warp: smem_elems u32 records, then 2 x smem_elems u16 stopper positions
+  uint32_t *my_list = lists + (size_t)warp * p.smem_elems * 2;
+  uint16_t *my_scratch = reinterpret_cast<uint16_t *>(my_list + p.smem_elems);
   while (true) {
     uint32_t run = 0;
     if (lane == 0) run = atomicAdd(p.run_counter, 1u);
@@ -338,16 +388,18 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
       continue;
     }
     if (n <= p.smem_elems && n < kCarriedFlag) {
-      merge_run<uint32_t>(p, my_list, n_new, n_old, qf, ql, lane);
+      merge_run<uint32_t, uint16_t>(p, my_list, my_scratch, n_new, n_old, qf, ql, lane);
     } else {
       unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(p.big_cursor, (unsigned long long)n);
+      if (lane == 0) base = atomicAdd(p.big_cursor, 2ull * n);   // n records + 2 n u32 positions
       base = __shfl_sync(kFull, base, 0);
-      if (base + n > p.big_capacity) {
+      if (base + 2ull * n > p.big_capacity) {
         if (lane == 0) { atomicExch(p.error, 1); p.new_cnt[ql] = 0; }
         continue;
       }
-      merge_run<unsigned long long>(p, p.big_scratch + base, n_new, n_old, qf, ql, lane);
+      merge_run<unsigned long long, uint32_t>(p, p.big_scratch + base,
+                                              reinterpret_cast<uint32_t *>(p.big_scratch + base + n),
+                                              n_new, n_old, qf, ql, lane);
     }
   }
 }
@@ -519,14 +571,14 @@ cudaError_t collect_pending_launch(const gm_hit *hits, const uint32_t *counts, u
   return cudaGetLastError();
 }
 
-size_t merge_smem_bytes(uint32_t elems_per_warp) { return (size_t)kMergeWarps * elems_per_warp * 4; }
+size_t merge_smem_bytes(uint32_t elems_per_warp) { return (size_t)kMergeWarps * elems_per_warp * 8; }
 
 cudaError_t merge_launch(const MergeParams &p, int sm_count, cudaStream_t stream) {
   const size_t smem = merge_smem_bytes(p.smem_elems);
   cudaError_t err =
       cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  merge_kernel<<<sm_count * 2, kMergeThreads, smem, stream>>>(p);
+  merge_kernel<<<sm_count, kMergeThreads, smem, stream>>>(p);   // 192 KB of lists: one CTA per SM
   return cudaGetLastError();
 }
 

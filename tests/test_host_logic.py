@@ -288,3 +288,53 @@ def test_shard_over_gloo_world2(tmp_path):
                           str(script)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
     assert out.stdout.count("SHARD_OK") == 2
+
+
+def test_parallel_partition_identity():
+    """The identity the device Merge uses to run libstdc++'s __unguarded_partition on a whole warp
+    (merge_traceback.cu, WarpLazySort): with L_k the k-th position from the left whose key is <=
+    the pivot's and R_k the k-th from the right whose key is >= it, the sequential loop performs
+    exactly the swaps L_k <-> R_k for k <= K = #{k: L_k < R_k} and returns L_1 if K == 0 else
+    min(L_{K+1}, R_K).  Checked against the sequential loop on tie-heavy inputs."""
+    rng = np.random.default_rng(0)
+
+    def sequential(a, f, l):
+        a = list(a)
+        pk, first, last = a[f][0], f + 1, l
+        while True:
+            while a[first][0] > pk:
+                first += 1
+            last -= 1
+            while pk > a[last][0]:
+                last -= 1
+            if not first < last:
+                return first, a
+            a[first], a[last] = a[last], a[first]
+            first += 1
+
+    def parallel(a, f, l):
+        a = list(a)
+        pk = a[f][0]
+        L = [i for i in range(f + 1, l) if a[i][0] <= pk]
+        rasc = [i for i in range(f + 1, l) if a[i][0] >= pk]
+        R = rasc[::-1]
+        K = 0
+        while K < min(len(L), len(R)) and L[K] < R[K]:
+            K += 1
+        for k in range(K):
+            a[L[k]], a[R[k]] = a[R[k]], a[L[k]]
+        cut = L[0] if K == 0 else min(L[K] if K < len(L) else 1 << 60, R[K - 1])
+        return cut, a
+
+    for _ in range(3000):
+        n, spread = int(rng.integers(17, 300)), int(rng.integers(1, 9))
+        a = [(int(k), i) for i, k in enumerate(rng.integers(0, spread, size=n))]
+        f, l = 0, n
+        x, y, z = f + 1, f + (l - f) // 2, l - 1          # __move_median_to_first
+        gt = lambda i, j: a[i][0] > a[j][0]
+        if gt(x, y):
+            m = y if gt(y, z) else (z if gt(x, z) else x)
+        else:
+            m = x if gt(x, z) else (z if gt(y, z) else y)
+        a[f], a[m] = a[m], a[f]
+        assert sequential(a, f, l) == parallel(a, f, l)
