@@ -269,8 +269,9 @@ class Context:
         self._check(self.L.gm_results_download(self.h, _ptr(hits), _ptr(counts)))
         return hits, counts
 
-    def set_search_variant(self, fast: bool):
-        self._check(self.L.gm_set_search_variant(self.h, int(fast)))
+    def set_search_variant(self, variant: int):
+        """2 = bucket kernel (default), 1 = sweep kernel, 0 = generic kernels."""
+        self._check(self.L.gm_set_search_variant(self.h, int(variant)))
 
     def set_deferred_traceback(self, on: bool):
         self._check(self.L.gm_set_deferred_traceback(self.h, int(on)))

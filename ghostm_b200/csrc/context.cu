@@ -20,6 +20,9 @@ cudaError_t sw_extend_s32_launch(const SwParams &p, int sm_count, cudaStream_t s
 uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions, bool fast);
 bool search_uses_fast(uint32_t list_len, bool allow_fast);
 cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream, bool allow_fast);
+bool search_bucket_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions, uint32_t *tile_bits);
+int search_bucket_grid(int sm_count);
+cudaError_t seed_search_bucket_launch(const SearchParams &p, int sm_count, cudaStream_t stream);
 int search_max_list_len();
 int search_max_threshold();
 size_t merge_smem_bytes(uint32_t elems_per_warp);
@@ -231,13 +234,16 @@ struct gm_context {
   DevBuf<uint32_t> cand_off, cand_cnt, cand_start, cand_score, cand_end;
   DevBuf<uint32_t> staging;
   uint32_t staging_cap = 1u << 15;
+  DevBuf<uint16_t> buckets;           // bucket seed search: [grid][tiles][bucket_cap] marks
+  DevBuf<uint32_t> fallback;          // queries the bucket kernel hands to the sweep kernel
+  uint32_t bucket_cap = 384;
   DevBuf<uint32_t> prefix;            // scan output (n_queries + 1)
   DevBuf<uint32_t> bounds;            // gm_candidates_pack part boundaries
   DevBuf<uint32_t> gather0, gather1, gather2;
   DevBuf<uint32_t> strip_scratch;
   DevBuf<unsigned long long> counters;  // [0] cand cursor [1] positions visited [2] cells [3] big cursor
   DevBuf<uint32_t> small;               // [0] query counter [1] task counter [2] overflow [3] n_jobs
-                                        // [4] merge error [5] run counter
+                                        // [4] merge error [5] run counter [6] search fallbacks
   uint64_t cand_total = 0;
   std::vector<uint32_t> h_counts;
 
@@ -252,10 +258,12 @@ struct gm_context {
   DevBuf<ChunkRef> chunk_tab;
   bool chunk_tab_dirty = true;
   bool search_fast = true;   // balanced register-resident search kernel when the options allow it
+  bool search_bucket = true; // bucket kernel (threshold 2) in front of it
   bool traceback_fast = true;
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits
   uint32_t serial = 0;
+  uint64_t search_fallbacks = 0;   // queries redone by the sweep kernel (bucket capacities exceeded)
 };
 
 namespace {
@@ -351,7 +359,7 @@ extern "C" void gm_destroy(gm_context *c) {
   c->matrix.release(); c->queries.release(); c->run_first.release(); c->run_last.release();
   c->cand_off.release(); c->cand_cnt.release(); c->cand_start.release(); c->cand_score.release();
   c->cand_end.release(); c->staging.release(); c->prefix.release(); c->gather0.release();
-  c->gather1.release(); c->gather2.release(); c->bounds.release(); c->strip_scratch.release(); c->counters.release();
+  c->gather1.release(); c->gather2.release(); c->bounds.release(); c->buckets.release(); c->fallback.release(); c->strip_scratch.release(); c->counters.release();
   c->small.release(); c->hits[0].release(); c->hits[1].release(); c->hit_cnt[0].release();
   c->hit_cnt[1].release(); c->jobs.release(); c->big_scratch.release(); c->tb_work.release(); c->chunk_tab.release();
   for (auto &e : c->ev) cudaEventDestroy(e);
@@ -560,8 +568,37 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     p.positions_visited = c->counters.p + 1;
     p.overflow = reinterpret_cast<int *>(c->small.p + 2);
     p.debug = getenv("GM_SEARCH_DEBUG") ? (uint32_t)atoi(getenv("GM_SEARCH_DEBUG")) : 0u;
+    uint32_t tile_bits = 0, launches = 1;
+    const bool bucket = c->search_bucket && c->search_fast &&
+                        search_bucket_ok(p.threshold, p.list_len, p.n_regions, &tile_bits);
+    if (bucket) {
+      const uint32_t n_tiles = (p.n_regions + (1u << tile_bits) - 1) >> tile_bits;
+      const int bgrid = search_bucket_grid(c->sm_count);
+      GM_CUDA(c->buckets.ensure((size_t)bgrid * n_tiles * c->bucket_cap));
+      GM_CUDA(c->fallback.ensure(c->n_queries));
+      p.tile_bits = tile_bits;
+      p.bucket_cap = c->bucket_cap;
+      p.buckets = c->buckets.p;
+      p.fallback_list = c->fallback.p;
+      p.fallback_n = c->small.p + 6;
+    }
     GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    GM_CUDA(seed_search_launch(p, grid, c->stream, c->search_fast));
+    if (bucket) {
+      GM_CUDA(seed_search_bucket_launch(p, c->sm_count, c->stream));
+      uint32_t n_fb = 0;
+      GM_CUDA(cudaMemcpyAsync(&n_fb, c->small.p + 6, 4, cudaMemcpyDeviceToHost, c->stream));
+      GM_CUDA(cudaStreamSynchronize(c->stream));
+      if (n_fb) {   // queries beyond the bucket kernel's capacities: the sweep kernel, same results
+        GM_CUDA(cudaMemsetAsync(c->small.p + 0, 0, 4, c->stream));
+        p.query_list = c->fallback.p;
+        p.n_queries = n_fb;
+        GM_CUDA(seed_search_launch(p, grid, c->stream, true));
+        ++launches;
+      }
+      c->search_fallbacks += n_fb;
+    } else {
+      GM_CUDA(seed_search_launch(p, grid, c->stream, c->search_fast));
+    }
     GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
     GM_CUDA(cudaMemcpyAsync(c->h_counts.data(), c->cand_cnt.p, (size_t)c->n_queries * 4,
                             cudaMemcpyDeviceToHost, c->stream));
@@ -575,7 +612,7 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
       float ms = 0;
       cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
       stats->ms_search += ms;
-      stats->kernel_launches += 1;
+      stats->kernel_launches += launches;
       unsigned long long v[2];
       GM_CUDA(cudaMemcpy(v, c->counters.p, sizeof(v), cudaMemcpyDeviceToHost));
       stats->seed_positions += v[1];
@@ -864,6 +901,7 @@ int run_traceback(gm_context *c, gm_hit *hits) {
 extern "C" int gm_set_search_variant(gm_context *c, int fast) {
   if (int r = check_ctx(c)) return r;
   c->search_fast = fast != 0;
+  c->search_bucket = fast >= 2;
   c->traceback_fast = fast != 0;
   return 0;
 }

@@ -63,6 +63,13 @@ struct SearchParams {
   unsigned long long *positions_visited;
   int *overflow;               // set when cand_capacity is exceeded
   uint32_t debug;              // timing experiments only (GM_SEARCH_DEBUG), 0 in production
+  const uint32_t *query_list;  // sweep kernels: process query_list[0..n_queries) instead of 0..n_queries
+  // bucket kernel (threshold 2)
+  uint32_t tile_bits;          // log2 regions per tile
+  uint32_t bucket_cap;         // marks per tile bucket
+  uint16_t *buckets;           // [gridDim.x][n_tiles][bucket_cap], L2-resident scratch
+  uint32_t *fallback_list;     // queries that exceed a capacity, redone by the sweep kernel
+  uint32_t *fallback_n;
 };
 
 // ---- merge / traceback --------------------------------------------------------------

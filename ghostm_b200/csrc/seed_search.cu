@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_kernel(const Se
   while (true) {
     if (tid == 0) sh.query = atomicAdd(p.query_counter, 1u);
     __syncthreads();
-    const uint32_t q = sh.query;
-    if (q >= p.n_queries) break;
+    if (sh.query >= p.n_queries) break;
+    const uint32_t q = p.query_list ? p.query_list[sh.query] : sh.query;
     const uint8_t *query = p.queries + (size_t)q * p.query_len;
 
     uint32_t *out = staging;
@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
   while (true) {
     if (tid == 0) sh.query = atomicAdd(p.query_counter, 1u);
     __syncthreads();
-    const uint32_t q = sh.query;
-    if (q >= p.n_queries) break;
+    if (sh.query >= p.n_queries) break;
+    const uint32_t q = p.query_list ? p.query_list[sh.query] : sh.query;
     const uint8_t *query = p.queries + (size_t)q * p.query_len;
 
     uint32_t *out = staging;
@@ -624,6 +624,303 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
   if (tid == 0 && sh.visited) atomicAdd(p.positions_visited, sh.visited);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bucket path (threshold 2, list_len <= 64): no shared-memory sweep of the region space, no slice
+// boundaries, no per-tile block barriers.  Per query, with the region space cut into <= 512
+// tiles of 2^tile_bits regions:
+//   phase A  the CTA streams ALL positions of the query's lists once, in balanced 32-position
+//            chunks (chunk k -> list via a per-query table); a position that starts a
+//            (list, region) run becomes a MARK and is appended as a 16-bit in-tile region to its
+//            tile's bucket (shared-memory atomicAdd for the slot; the buckets live in an
+//            L2-resident per-CTA scratch, 2 B per mark);
+//   phase B  every WARP owns whole tiles (dynamic fetch): it reads the tile's bucket, sets the
+//            marks in its PRIVATE occupancy bitmap (atomicOr returns whether the region was hit
+//            before = two lists), then decides per mark: a region d emits iff it was hit twice or
+//            region d+1 is occupied (threshold 2: cnt(d) + cnt(d+1) >= 2 with cnt(d) >= 1), sets
+//            the private emit bitmap, clears what it touched and appends the tile's candidates,
+//            ascending, to the CTA's staging area.  Only __syncwarp inside a tile;
+//   phase C  an exclusive scan over the per-tile counts orders the tiles; the candidates are
+//            copied to the query's slice of the global candidate buffer (one atomicAdd).
+// Region 0 of tile t+1 vouches for the last region of tile t through a per-tile halo bit.
+// Queries that do not fit the fixed capacities (a bucket, the chunk table, the staging area -
+// low-complexity queries against repetitive databases) are queued for the sweep kernel above,
+// which has no such limits; the results are identical either way.
+constexpr int kBkThreads = 384;
+constexpr int kBkWarps = kBkThreads / 32;
+constexpr int kBkMaxTiles = 512;
+constexpr int kBkMaxChunks = 4096;      // 32-position chunks per query
+constexpr int kBkLists = 64;
+constexpr int kBkSlots = 8;             // register-resident marks per lane per tile
+constexpr int kBkUnroll = 4;            // chunks in flight per warp in phase A
+constexpr uint32_t kBkMaxTileBits = 15;
+constexpr uint32_t kBkMinTileBits = 10;
+
+struct BucketShared {
+  uint32_t lbeg[kBkLists], lend[kBkLists];
+  uint32_t pre[kBkLists + 1];             // exclusive prefix of chunks per list
+  uint32_t cnt[kBkMaxTiles];              // marks per tile; phase C: output offset of the tile
+  uint32_t tile_off[kBkMaxTiles];         // staging offset of the tile's candidates
+  uint32_t tile_cnt[kBkMaxTiles];
+  uint32_t halo[kBkMaxTiles / 32 + 1];    // bit t: region 0 of tile t is occupied
+  uint8_t chunk_list[kBkMaxChunks];
+  uint32_t query, next_tile, stage_n, bad;
+  unsigned long long base;
+  unsigned long long visited;
+};
+
+__global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const SearchParams p) {
+  extern __shared__ __align__(16) uint32_t dyn[];
+  __shared__ BucketShared sh;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t r = p.log_region, TB = p.tile_bits, xmask = (1u << TB) - 1u;
+  const uint32_t W = 1u << (TB - 5);                     // words per private bitmap
+  const uint32_t n_tiles = (p.n_regions + xmask) >> TB;
+  const uint32_t S = p.bucket_cap;
+  uint32_t *occ = dyn + (size_t)warp * (2 * W + 1);       // [W + 1]: +1 halo word
+  uint32_t *emitb = occ + W + 1;                          // [W]
+  uint16_t *bucket = p.buckets + (size_t)blockIdx.x * n_tiles * S;
+  uint32_t *stage = p.staging + (size_t)blockIdx.x * p.staging_cap;
+
+  for (uint32_t i = tid; i < kBkWarps * (2 * W + 1); i += kBkThreads) dyn[i] = 0;
+  if (tid == 0) sh.visited = 0;
+  __syncthreads();
+
+  while (true) {
+    if (tid == 0) sh.query = atomicAdd(p.query_counter, 1u);
+    __syncthreads();
+    const uint32_t q = sh.query;
+    if (q >= p.n_queries) break;
+    const uint8_t *query = p.queries + (size_t)q * p.query_len;
+
+    // ---- phase 0: intervals (index.h:105-114), chunk table, counters
+    if (tid < p.list_len) {
+      const uint32_t j = tid, off = j * p.shift;
+      const uint32_t key = get_key(query + off, p.seed);
+      uint32_t b = p.keys_count[key];
+      const uint32_t e = p.keys_count[key + 1];
+      while (b < e && p.positions[b] < off) ++b;                      // aligner.cpp:430-431
+      sh.lbeg[j] = b;
+      sh.lend[j] = e;
+      if (e > b) atomicAdd(&sh.visited, (unsigned long long)(e - b));
+    }
+    for (uint32_t t = tid; t < n_tiles; t += kBkThreads) { sh.cnt[t] = 0; sh.tile_cnt[t] = 0; }
+    if (tid < kBkMaxTiles / 32 + 1) sh.halo[tid] = 0;
+    if (tid == 0) { sh.next_tile = 0; sh.stage_n = 0; sh.bad = 0; }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t carry = 0;
+      for (uint32_t j0 = 0; j0 < p.list_len; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const uint32_t c = j < p.list_len ? (sh.lend[j] - sh.lbeg[j] + 31) / 32 : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (j < p.list_len) sh.pre[j] = carry + incl - c;
+        carry += __shfl_sync(kFull, incl, 31);
+      }
+      if (lane == 0) sh.pre[p.list_len] = carry;
+    }
+    __syncthreads();
+    const uint32_t C = sh.pre[p.list_len];
+    bool bad = C > kBkMaxChunks;
+    if (!bad) {
+      for (uint32_t k = tid; k < C; k += kBkThreads) {
+        uint32_t lo = 0, hi = p.list_len;      // pre[lo] <= k < pre[hi]
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (sh.pre[mid] <= k) lo = mid; else hi = mid;
+        }
+        sh.chunk_list[k] = (uint8_t)lo;
+      }
+      __syncthreads();
+
+      // ---- phase A: marks -> tile buckets
+      for (uint32_t k0 = warp; k0 < C; k0 += kBkWarps * kBkUnroll) {
+        uint32_t pos[kBkUnroll], prev[kBkUnroll], offs[kBkUnroll];
+#pragma unroll
+        for (int u = 0; u < kBkUnroll; ++u) {
+          const uint32_t k = k0 + u * kBkWarps;
+          pos[u] = kNone;
+          prev[u] = kNone;
+          offs[u] = 0;
+          if (k < C) {
+            const uint32_t j = sh.chunk_list[k];
+            const uint32_t b = sh.lbeg[j];
+            const uint32_t idx = b + 32u * (k - sh.pre[j]) + lane;
+            offs[u] = j * p.shift;
+            if (idx < sh.lend[j]) {
+              pos[u] = __ldg(p.positions + idx);
+              if (idx > b) prev[u] = __ldg(p.positions + idx - 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kBkUnroll; ++u) {
+          if (pos[u] == kNone) continue;
+          const uint32_t d = (pos[u] - offs[u]) >> r;
+          if (prev[u] != kNone && ((prev[u] - offs[u]) >> r) == d) continue;   // same list, same region
+          const uint32_t t = d >> TB, x = d & xmask;
+          const uint32_t slot = atomicAdd(&sh.cnt[t], 1u);
+          if (slot < S) bucket[(size_t)t * S + slot] = (uint16_t)x;
+          else sh.bad = 1;
+          if (x == 0) atomicOr(&sh.halo[t >> 5], 1u << (t & 31));
+        }
+      }
+      __syncthreads();
+      bad = sh.bad != 0;
+    }
+
+    if (!bad) {
+      // ---- phase B: one warp per tile
+      while (true) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&sh.next_tile, 1u);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= n_tiles) break;
+        const uint32_t n = sh.cnt[t];
+        if (n == 0) continue;
+        uint16_t *bk = bucket + (size_t)t * S;
+        if (lane == 0)
+          occ[W] = (t + 1 < n_tiles) ? (sh.halo[(t + 1) >> 5] >> ((t + 1) & 31)) & 1u : 0u;
+        // arrive: bit 31 of a mark = the region was already hit (by another list)
+        uint32_t m[kBkSlots];
+#pragma unroll
+        for (int s = 0; s < kBkSlots; ++s) {
+          const uint32_t i = s * 32 + lane;
+          m[s] = kNone;
+          if (i < n) {
+            const uint32_t x = bk[i];
+            const uint32_t old = atomicOr(&occ[x >> 5], 1u << (x & 31));
+            m[s] = x | (((old >> (x & 31)) & 1u) << 31);
+          }
+        }
+        for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) {   // beyond the register slots
+          const uint32_t x = bk[i];
+          const uint32_t old = atomicOr(&occ[x >> 5], 1u << (x & 31));
+          bk[i] = (uint16_t)(x | (((old >> (x & 31)) & 1u) << 15));  // x < 2^15: bit 15 is free
+        }
+        __syncwarp();
+        // decide
+        uint32_t summ = 0;
+        bool r1 = false;
+#pragma unroll
+        for (int s = 0; s < kBkSlots; ++s) {
+          if (m[s] == kNone) continue;
+          const uint32_t x = m[s] & 0x7FFFFFFFu, dbl = m[s] >> 31, y = x + 1;
+          const uint32_t right = (occ[y >> 5] >> (y & 31)) & 1u;
+          if (dbl | right) {
+            atomicOr(&emitb[x >> 5], 1u << (x & 31));
+            summ |= 1u << (x >> 10);
+          }
+          r1 |= x == 1 && dbl;
+        }
+        for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) {
+          const uint32_t v = bk[i], x = v & 0x7FFFu, dbl = v >> 15, y = x + 1;
+          const uint32_t right = (occ[y >> 5] >> (y & 31)) & 1u;
+          if (dbl | right) {
+            atomicOr(&emitb[x >> 5], 1u << (x & 31));
+            summ |= 1u << (x >> 10);
+          }
+          r1 |= x == 1 && dbl;
+        }
+        // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an unoccupied
+        // region 0 still emits when region 1 alone reaches the threshold.
+        const bool virt = t == 0 && __any_sync(kFull, r1) && !(occ[0] & 1u);
+        __syncwarp();
+        if (virt && lane == 0) { emitb[0] |= 1u; summ |= 1u; }
+        // clear the occupancy bits this tile set
+#pragma unroll
+        for (int s = 0; s < kBkSlots; ++s)
+          if (m[s] != kNone) occ[(m[s] & 0x7FFFFFFFu) >> 5] = 0;
+        for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) occ[(bk[i] & 0x7FFFu) >> 5] = 0;
+        if (lane == 0) occ[W] = 0;
+        summ = __reduce_or_sync(kFull, summ);
+        __syncwarp();
+        if (summ) {
+          // ordered output of the (sparse) emit bitmap: groups of 32 words = 1024 regions
+          uint32_t total = 0;
+          for (uint32_t gb = summ; gb; gb &= gb - 1)
+            total += __popc(emitb[(__ffs(gb) - 1) * 32 + lane]);
+          total = __reduce_add_sync(kFull, total);
+          uint32_t off = 0;
+          if (lane == 0) off = atomicAdd(&sh.stage_n, total);
+          off = __shfl_sync(kFull, off, 0);
+          if (lane == 0) { sh.tile_off[t] = off; sh.tile_cnt[t] = total; }
+          for (uint32_t gb = summ; gb; gb &= gb - 1) {
+            const uint32_t g = __ffs(gb) - 1;
+            uint32_t bits = emitb[g * 32 + lane];
+            emitb[g * 32 + lane] = 0;
+            const uint32_t c = __popc(bits);
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t v = __shfl_up_sync(kFull, incl, o);
+              if (lane >= o) incl += v;
+            }
+            uint32_t slot = off + incl - c;
+            while (bits) {
+              const uint32_t bpos = __ffs(bits) - 1;
+              bits &= bits - 1;
+              if (slot < p.staging_cap) stage[slot] = ((t << TB) + g * 1024 + lane * 32 + bpos) << r;
+              ++slot;
+            }
+            off += __shfl_sync(kFull, incl, 31);
+          }
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      bad = sh.stage_n > p.staging_cap;
+    }
+
+    if (bad) {   // exceeds a fixed capacity: the sweep kernel redoes this query (planes are clean)
+      if (tid == 0) {
+        p.fallback_list[atomicAdd(p.fallback_n, 1u)] = q;
+        p.cand_off[q] = 0;
+        p.cand_cnt[q] = 0;
+      }
+      continue;
+    }
+
+    // ---- phase C: order the tiles, hand the candidates over
+    const uint32_t n = sh.stage_n;
+    if (warp == 0) {
+      uint32_t carry = 0;
+      for (uint32_t t0 = 0; t0 < n_tiles; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const uint32_t c = t < n_tiles ? sh.tile_cnt[t] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (t < n_tiles) sh.cnt[t] = carry + incl - c;
+        carry += __shfl_sync(kFull, incl, 31);
+      }
+      if (lane == 0) {
+        sh.base = n ? atomicAdd(p.cand_cursor, (unsigned long long)n) : 0ull;
+        const bool fits = sh.base + n <= p.cand_capacity;
+        if (n && !fits) atomicExch(p.overflow, 1);
+        p.cand_off[q] = (uint32_t)sh.base;
+        p.cand_cnt[q] = fits ? n : 0u;
+      }
+    }
+    __syncthreads();
+    const unsigned long long cbase = sh.base;
+    if (n && cbase + n <= p.cand_capacity) {
+      for (uint32_t t = warp; t < n_tiles; t += kBkWarps) {
+        const uint32_t c = sh.tile_cnt[t], src = sh.tile_off[t], dst = sh.cnt[t];
+        for (uint32_t i = lane; i < c; i += 32) p.cand_start[cbase + dst + i] = stage[src + i];
+      }
+    }
+  }
+  if (tid == 0 && sh.visited) atomicAdd(p.positions_visited, sh.visited);
+}
+
 // Generic dynamic shared memory size for a tile of M regions.
 size_t search_smem_bytes(int planes, uint32_t M) {   // count planes + the emit bitmap + summary
   const uint32_t words = M / 32 + 1;
@@ -677,6 +974,31 @@ cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t str
     default: return cudaErrorInvalidValue;
   }
 #undef GM_LAUNCH_SEARCH
+  return cudaGetLastError();
+}
+
+// ---- bucket path configuration
+bool search_bucket_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions, uint32_t *tile_bits) {
+  if (threshold != 2 || list_len > kBkLists) return false;
+  uint32_t tb = kBkMinTileBits;     // about 256 tiles, 2^10 .. 2^15 regions each
+  while (tb < kBkMaxTileBits && ((n_regions + (1u << tb) - 1) >> tb) > 256) ++tb;
+  if (((n_regions + (1u << tb) - 1) >> tb) > kBkMaxTiles) return false;
+  *tile_bits = tb;
+  return true;
+}
+
+size_t search_bucket_smem(uint32_t tile_bits) {
+  return (size_t)kBkWarps * (2 * (1u << (tile_bits - 5)) + 1) * sizeof(uint32_t);
+}
+
+int search_bucket_grid(int sm_count) { return sm_count * 2; }
+
+cudaError_t seed_search_bucket_launch(const SearchParams &p, int sm_count, cudaStream_t stream) {
+  const size_t smem = search_bucket_smem(p.tile_bits);
+  cudaError_t err = cudaFuncSetAttribute(seed_search_bucket_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  seed_search_bucket_kernel<<<search_bucket_grid(sm_count), kBkThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -185,10 +185,12 @@ int gm_results_upload(gm_context *ctx, const gm_hit *hits, const uint32_t *count
  * context.  gm_results_download calls it implicitly.  on = 0 restores the reference order
  * (TraceBack inside every Merge). */
 int gm_set_deferred_traceback(gm_context *ctx, int on);
-/* Kernel variants: 1 (default) = balanced register-resident seed-search kernel whenever
- * list_len <= 64 and register-resident TraceBack whenever L <= 80, else the generic kernels;
- * 0 = always the generic kernels (tests). */
-int gm_set_search_variant(gm_context *ctx, int fast);
+/* Kernel variants: 2 (default) = bucket seed-search kernel when threshold == 2 and
+ * list_len <= 64 (queries beyond its capacities are redone by the sweep kernel), else as 1;
+ * 1 = balanced register-resident sweep kernel whenever list_len <= 64 and register-resident
+ * TraceBack whenever L <= 80, else the generic kernels; 0 = always the generic kernels (tests).
+ * All variants produce identical candidates. */
+int gm_set_search_variant(gm_context *ctx, int variant);
 int gm_traceback_pending(gm_context *ctx, uint64_t *n_done, gm_stats *stats);
 /* Empty the device hit lists without re-uploading the queries. */
 int gm_results_clear(gm_context *ctx);
