@@ -173,6 +173,7 @@ struct WarpLazySort {
   }
 
   __device__ void loop_next_block(uint32_t lane) {  // __introsort_loop on the leftmost pending range
+    if (sp == 0) { looped = n; return; }   // cannot happen: the frames always cover [looped, n)
     const Frame fr = stack[--sp];
     int f = fr.first, l = fr.last, depth = fr.depth;
     while (l - f > 16) {
@@ -270,6 +271,7 @@ __device__ uint32_t db_get_id(const uint32_t *pos, uint32_t n_seqs, uint32_t seq
     const uint32_t idx = lo + lane * step;
     const bool ok = idx < hi && pos[idx] <= position;
     const uint32_t b = __ballot_sync(kFull, ok);
+    if (b == 0) return kNoId;              // cannot happen: pos[lo] <= position is invariant
     const uint32_t nlo = lo + (31 - __clz(b)) * step;
     hi = hi < nlo + step ? hi : nlo + step;
     lo = nlo;
