@@ -628,30 +628,32 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
 // Bucket path (threshold 2, list_len <= 64): no shared-memory sweep of the region space, no slice
 // boundaries, no per-tile block barriers.  Per query, with the region space cut into <= 512
 // tiles of 2^tile_bits regions:
-//   phase A  the CTA streams ALL positions of the query's lists once, in balanced 32-position
-//            chunks (chunk k -> list via a per-query table); a position that starts a
-//            (list, region) run becomes a MARK and is appended as a 16-bit in-tile region to its
-//            tile's bucket (shared-memory atomicAdd for the slot; the buckets live in an
-//            L2-resident per-CTA scratch, 2 B per mark);
-//   phase B  every WARP owns whole tiles (dynamic fetch): it reads the tile's bucket, sets the
-//            marks in its PRIVATE occupancy bitmap (atomicOr returns whether the region was hit
-//            before = two lists), then decides per mark: a region d emits iff it was hit twice or
-//            region d+1 is occupied (threshold 2: cnt(d) + cnt(d+1) >= 2 with cnt(d) >= 1), sets
-//            the private emit bitmap, clears what it touched and appends the tile's candidates,
-//            ascending, to the CTA's staging area.  Only __syncwarp inside a tile;
+//   phase A  the CTA streams ALL positions of the query's lists once, list by list, in 32-position
+//            chunks dealt round robin to the warps (global chunk number mod warps, so the skewed
+//            list lengths stay balanced while every per-list value is hoisted out of the chunk
+//            loop); a position that starts a (list, region) run becomes a MARK and is appended as
+//            a 16-bit in-tile region to its tile's bucket (shared-memory atomicAdd for the slot;
+//            the buckets live in an L2-resident per-CTA scratch, 2 B per mark);
+//   phase B  every WARP owns whole tiles (dynamic fetch): it reads the tile's bucket and sets the
+//            marks in its PRIVATE occupancy bitmap; the first mark to arrive at a region owns it,
+//            later ones (other lists) set the region's bit in a second bitmap.  An owner emits
+//            its region d iff it was hit twice or region d+1 is occupied (threshold 2:
+//            cnt(d) + cnt(d+1) >= 2 with cnt(d) >= 1) - exactly one emitter per region, so the few
+//            emitted regions of a tile are ordered by counting ranks, no bitmap scan.  Only
+//            __syncwarp inside a tile;
 //   phase C  an exclusive scan over the per-tile counts orders the tiles; the candidates are
 //            copied to the query's slice of the global candidate buffer (one atomicAdd).
 // Region 0 of tile t+1 vouches for the last region of tile t through a per-tile halo bit.
-// Queries that do not fit the fixed capacities (a bucket, the chunk table, the staging area -
+// Queries that do not fit the fixed capacities (a bucket, a tile's emit list, the staging area -
 // low-complexity queries against repetitive databases) are queued for the sweep kernel above,
 // which has no such limits; the results are identical either way.
 constexpr int kBkThreads = 384;
 constexpr int kBkWarps = kBkThreads / 32;
 constexpr int kBkMaxTiles = 512;
-constexpr int kBkMaxChunks = 4096;      // 32-position chunks per query
 constexpr int kBkLists = 64;
 constexpr int kBkSlots = 8;             // register-resident marks per lane per tile
 constexpr int kBkUnroll = 4;            // chunks in flight per warp in phase A
+constexpr int kBkEmitCap = 126;         // emitted regions per tile (u16 list, 64 words with its counter)
 constexpr uint32_t kBkMaxTileBits = 15;
 constexpr uint32_t kBkMinTileBits = 10;
 
@@ -662,7 +664,6 @@ struct BucketShared {
   uint32_t tile_off[kBkMaxTiles];         // staging offset of the tile's candidates
   uint32_t tile_cnt[kBkMaxTiles];
   uint32_t halo[kBkMaxTiles / 32 + 1];    // bit t: region 0 of tile t is occupied
-  uint8_t chunk_list[kBkMaxChunks];
   uint32_t query, next_tile, stage_n, bad;
   unsigned long long base;
   unsigned long long visited;
@@ -676,12 +677,14 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
   const uint32_t W = 1u << (TB - 5);                     // words per private bitmap
   const uint32_t n_tiles = (p.n_regions + xmask) >> TB;
   const uint32_t S = p.bucket_cap;
-  uint32_t *occ = dyn + (size_t)warp * (2 * W + 1);       // [W + 1]: +1 halo word
-  uint32_t *emitb = occ + W + 1;                          // [W]
+  uint32_t *occ = dyn + (size_t)warp * (2 * W + 1 + 64);  // [W + 1]: +1 halo word
+  uint32_t *multi = occ + W + 1;                          // [W] regions hit by >= 2 lists
+  uint32_t *elist_n = multi + W;                          // emit list: counter word + u16 regions
+  uint16_t *elist = reinterpret_cast<uint16_t *>(elist_n + 1);
   uint16_t *bucket = p.buckets + (size_t)blockIdx.x * n_tiles * S;
   uint32_t *stage = p.staging + (size_t)blockIdx.x * p.staging_cap;
 
-  for (uint32_t i = tid; i < kBkWarps * (2 * W + 1); i += kBkThreads) dyn[i] = 0;
+  for (uint32_t i = tid; i < kBkWarps * (2 * W + 1 + 64); i += kBkThreads) dyn[i] = 0;
   if (tid == 0) sh.visited = 0;
   __syncthreads();
 
@@ -692,7 +695,7 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
     if (q >= p.n_queries) break;
     const uint8_t *query = p.queries + (size_t)q * p.query_len;
 
-    // ---- phase 0: intervals (index.h:105-114), chunk table, counters
+    // ---- phase 0: intervals (index.h:105-114), chunk prefix, counters
     if (tid < p.list_len) {
       const uint32_t j = tid, off = j * p.shift;
       const uint32_t key = get_key(query + off, p.seed);
@@ -724,54 +727,40 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
       if (lane == 0) sh.pre[p.list_len] = carry;
     }
     __syncthreads();
-    const uint32_t C = sh.pre[p.list_len];
-    bool bad = C > kBkMaxChunks;
-    if (!bad) {
-      for (uint32_t k = tid; k < C; k += kBkThreads) {
-        uint32_t lo = 0, hi = p.list_len;      // pre[lo] <= k < pre[hi]
-        while (hi - lo > 1) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (sh.pre[mid] <= k) lo = mid; else hi = mid;
-        }
-        sh.chunk_list[k] = (uint8_t)lo;
-      }
-      __syncthreads();
 
-      // ---- phase A: marks -> tile buckets
-      for (uint32_t k0 = warp; k0 < C; k0 += kBkWarps * kBkUnroll) {
-        uint32_t pos[kBkUnroll], prev[kBkUnroll], offs[kBkUnroll];
+    // ---- phase A: marks -> tile buckets
+    for (uint32_t j = 0; j < p.list_len; ++j) {
+      const uint32_t b = sh.lbeg[j], e = sh.lend[j], off = j * p.shift;
+      const uint32_t nj = (e - b + 31) / 32;
+      // this warp's chunks of list j: global chunk number (pre[j] + c) % warps == warp
+      const uint32_t c0 = (warp + kBkWarps - sh.pre[j] % kBkWarps) % kBkWarps;
+      for (uint32_t c = c0; c < nj; c += kBkWarps * kBkUnroll) {
+        uint32_t pos[kBkUnroll], prev[kBkUnroll];
 #pragma unroll
         for (int u = 0; u < kBkUnroll; ++u) {
-          const uint32_t k = k0 + u * kBkWarps;
+          const uint32_t idx = b + 32u * (c + u * kBkWarps) + lane;
           pos[u] = kNone;
           prev[u] = kNone;
-          offs[u] = 0;
-          if (k < C) {
-            const uint32_t j = sh.chunk_list[k];
-            const uint32_t b = sh.lbeg[j];
-            const uint32_t idx = b + 32u * (k - sh.pre[j]) + lane;
-            offs[u] = j * p.shift;
-            if (idx < sh.lend[j]) {
-              pos[u] = __ldg(p.positions + idx);
-              if (idx > b) prev[u] = __ldg(p.positions + idx - 1);
-            }
+          if (idx < e) {
+            pos[u] = __ldg(p.positions + idx);
+            if (idx > b) prev[u] = __ldg(p.positions + idx - 1);
           }
         }
 #pragma unroll
         for (int u = 0; u < kBkUnroll; ++u) {
           if (pos[u] == kNone) continue;
-          const uint32_t d = (pos[u] - offs[u]) >> r;
-          if (prev[u] != kNone && ((prev[u] - offs[u]) >> r) == d) continue;   // same list, same region
+          const uint32_t d = (pos[u] - off) >> r;
+          if (prev[u] != kNone && ((prev[u] - off) >> r) == d) continue;   // same list, same region
           const uint32_t t = d >> TB, x = d & xmask;
           const uint32_t slot = atomicAdd(&sh.cnt[t], 1u);
-          if (slot < S) bucket[(size_t)t * S + slot] = (uint16_t)x;
+          if (slot < S) bucket[t * S + slot] = (uint16_t)x;
           else sh.bad = 1;
           if (x == 0) atomicOr(&sh.halo[t >> 5], 1u << (t & 31));
         }
       }
-      __syncthreads();
-      bad = sh.bad != 0;
     }
+    __syncthreads();
+    bool bad = sh.bad != 0;
 
     if (!bad) {
       // ---- phase B: one warp per tile
@@ -782,98 +771,90 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
         if (t >= n_tiles) break;
         const uint32_t n = sh.cnt[t];
         if (n == 0) continue;
-        uint16_t *bk = bucket + (size_t)t * S;
+        uint16_t *bk = bucket + t * S;
         if (lane == 0)
           occ[W] = (t + 1 < n_tiles) ? (sh.halo[(t + 1) >> 5] >> ((t + 1) & 31)) & 1u : 0u;
-        // arrive: bit 31 of a mark = the region was already hit (by another list)
+        // arrive: the first mark at a region owns it (bit 31 of m), later ones flag it in `multi`
         uint32_t m[kBkSlots];
 #pragma unroll
         for (int s = 0; s < kBkSlots; ++s) {
           const uint32_t i = s * 32 + lane;
           m[s] = kNone;
           if (i < n) {
-            const uint32_t x = bk[i];
-            const uint32_t old = atomicOr(&occ[x >> 5], 1u << (x & 31));
-            m[s] = x | (((old >> (x & 31)) & 1u) << 31);
+            const uint32_t x = bk[i], bit = 1u << (x & 31);
+            const uint32_t old = atomicOr(&occ[x >> 5], bit);
+            m[s] = x;
+            if (old & bit) atomicOr(&multi[x >> 5], bit);
+            else m[s] = x | 0x80000000u;
           }
         }
         for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) {   // beyond the register slots
-          const uint32_t x = bk[i];
-          const uint32_t old = atomicOr(&occ[x >> 5], 1u << (x & 31));
-          bk[i] = (uint16_t)(x | (((old >> (x & 31)) & 1u) << 15));  // x < 2^15: bit 15 is free
+          const uint32_t x = bk[i], bit = 1u << (x & 31);
+          const uint32_t old = atomicOr(&occ[x >> 5], bit);
+          if (old & bit) atomicOr(&multi[x >> 5], bit);
+          else bk[i] = (uint16_t)(x | 0x8000u);                      // x < 2^15: bit 15 = owner
         }
         __syncwarp();
-        // decide
-        uint32_t summ = 0;
-        bool r1 = false;
+        // decide: owners only; emitted regions go to the warp's emit list (unordered)
 #pragma unroll
         for (int s = 0; s < kBkSlots; ++s) {
-          if (m[s] == kNone) continue;
-          const uint32_t x = m[s] & 0x7FFFFFFFu, dbl = m[s] >> 31, y = x + 1;
-          const uint32_t right = (occ[y >> 5] >> (y & 31)) & 1u;
-          if (dbl | right) {
-            atomicOr(&emitb[x >> 5], 1u << (x & 31));
-            summ |= 1u << (x >> 10);
+          if ((int)m[s] >= 0) continue;                              // not an owner / empty slot
+          const uint32_t x = m[s] & 0x7FFFFFFFu, y = x + 1;
+          if (((multi[x >> 5] >> (x & 31)) | (occ[y >> 5] >> (y & 31))) & 1u) {
+            const uint32_t i = atomicAdd(elist_n, 1u);
+            if (i < kBkEmitCap) elist[i] = (uint16_t)x;
           }
-          r1 |= x == 1 && dbl;
         }
         for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) {
-          const uint32_t v = bk[i], x = v & 0x7FFFu, dbl = v >> 15, y = x + 1;
-          const uint32_t right = (occ[y >> 5] >> (y & 31)) & 1u;
-          if (dbl | right) {
-            atomicOr(&emitb[x >> 5], 1u << (x & 31));
-            summ |= 1u << (x >> 10);
+          const uint32_t v = bk[i];
+          if (!(v & 0x8000u)) continue;
+          const uint32_t x = v & 0x7FFFu, y = x + 1;
+          if (((multi[x >> 5] >> (x & 31)) | (occ[y >> 5] >> (y & 31))) & 1u) {
+            const uint32_t k = atomicAdd(elist_n, 1u);
+            if (k < kBkEmitCap) elist[k] = (uint16_t)x;
           }
-          r1 |= x == 1 && dbl;
         }
         // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an unoccupied
         // region 0 still emits when region 1 alone reaches the threshold.
-        const bool virt = t == 0 && __any_sync(kFull, r1) && !(occ[0] & 1u);
+        const uint32_t virt = (t == 0 && !(occ[0] & 1u) && (multi[0] & 2u)) ? 1u : 0u;
         __syncwarp();
-        if (virt && lane == 0) { emitb[0] |= 1u; summ |= 1u; }
-        // clear the occupancy bits this tile set
+        // clear what this tile set
 #pragma unroll
-        for (int s = 0; s < kBkSlots; ++s)
-          if (m[s] != kNone) occ[(m[s] & 0x7FFFFFFFu) >> 5] = 0;
-        for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) occ[(bk[i] & 0x7FFFu) >> 5] = 0;
-        if (lane == 0) occ[W] = 0;
-        summ = __reduce_or_sync(kFull, summ);
+        for (int s = 0; s < kBkSlots; ++s) {
+          if (m[s] == kNone) continue;
+          const uint32_t w = (m[s] & 0x7FFFFFFFu) >> 5;
+          if ((int)m[s] < 0) occ[w] = 0; else multi[w] = 0;
+        }
+        for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) {
+          const uint32_t v = bk[i], w = (v & 0x7FFFu) >> 5;
+          if (v & 0x8000u) occ[w] = 0; else multi[w] = 0;
+        }
+        const uint32_t k = *elist_n;
         __syncwarp();
-        if (summ) {
-          // ordered output of the (sparse) emit bitmap: groups of 32 words = 1024 regions
-          uint32_t total = 0;
-          for (uint32_t gb = summ; gb; gb &= gb - 1)
-            total += __popc(emitb[(__ffs(gb) - 1) * 32 + lane]);
-          total = __reduce_add_sync(kFull, total);
+        if (lane == 0) { occ[W] = 0; *elist_n = 0; }
+        if (k > kBkEmitCap) {
+          if (lane == 0) sh.bad = 1;
+        } else if (k + virt) {
+          // exactly one entry per emitted region: its rank is the number of smaller entries
           uint32_t off = 0;
-          if (lane == 0) off = atomicAdd(&sh.stage_n, total);
+          if (lane == 0) {
+            off = atomicAdd(&sh.stage_n, k + virt);
+            sh.tile_off[t] = off;
+            sh.tile_cnt[t] = k + virt;
+          }
           off = __shfl_sync(kFull, off, 0);
-          if (lane == 0) { sh.tile_off[t] = off; sh.tile_cnt[t] = total; }
-          for (uint32_t gb = summ; gb; gb &= gb - 1) {
-            const uint32_t g = __ffs(gb) - 1;
-            uint32_t bits = emitb[g * 32 + lane];
-            emitb[g * 32 + lane] = 0;
-            const uint32_t c = __popc(bits);
-            uint32_t incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const uint32_t v = __shfl_up_sync(kFull, incl, o);
-              if (lane >= o) incl += v;
-            }
-            uint32_t slot = off + incl - c;
-            while (bits) {
-              const uint32_t bpos = __ffs(bits) - 1;
-              bits &= bits - 1;
-              if (slot < p.staging_cap) stage[slot] = ((t << TB) + g * 1024 + lane * 32 + bpos) << r;
-              ++slot;
-            }
-            off += __shfl_sync(kFull, incl, 31);
+          if (virt && lane == 0 && off < p.staging_cap) stage[off] = 0;   // region 0 of tile 0
+          for (uint32_t i = lane; i < k; i += 32) {
+            const uint32_t x = elist[i];
+            uint32_t rank = virt;
+            for (uint32_t i2 = 0; i2 < k; ++i2) rank += elist[i2] < x;
+            if (off + rank < p.staging_cap) stage[off + rank] = ((t << TB) + x) << r;
           }
         }
         __syncwarp();
       }
       __syncthreads();
-      bad = sh.stage_n > p.staging_cap;
+      bad = sh.bad != 0 || sh.stage_n > p.staging_cap;
     }
 
     if (bad) {   // exceeds a fixed capacity: the sweep kernel redoes this query (planes are clean)
@@ -988,7 +969,7 @@ bool search_bucket_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions,
 }
 
 size_t search_bucket_smem(uint32_t tile_bits) {
-  return (size_t)kBkWarps * (2 * (1u << (tile_bits - 5)) + 1) * sizeof(uint32_t);
+  return (size_t)kBkWarps * (2 * (1u << (tile_bits - 5)) + 1 + 64) * sizeof(uint32_t);
 }
 
 int search_bucket_grid(int sm_count) { return sm_count * 2; }
