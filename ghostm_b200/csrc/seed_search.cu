@@ -654,6 +654,7 @@ constexpr int kBkLists = 64;
 constexpr int kBkSlots = 8;             // register-resident marks per lane per tile
 constexpr int kBkUnroll = 4;            // chunks in flight per warp in phase A
 constexpr int kBkEmitCap = 126;         // emitted regions per tile (u16 list, 64 words with its counter)
+constexpr uint32_t kBkEmpty = 0x7FFFFFFFu;   // empty register slot: bit 31 (owner) clear, no valid region
 constexpr uint32_t kBkMaxTileBits = 15;
 constexpr uint32_t kBkMinTileBits = 10;
 
@@ -779,7 +780,7 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
 #pragma unroll
         for (int s = 0; s < kBkSlots; ++s) {
           const uint32_t i = s * 32 + lane;
-          m[s] = kNone;
+          m[s] = kBkEmpty;
           if (i < n) {
             const uint32_t x = bk[i], bit = 1u << (x & 31);
             const uint32_t old = atomicOr(&occ[x >> 5], bit);
@@ -821,7 +822,7 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
         // clear what this tile set
 #pragma unroll
         for (int s = 0; s < kBkSlots; ++s) {
-          if (m[s] == kNone) continue;
+          if (m[s] == kBkEmpty) continue;
           const uint32_t w = (m[s] & 0x7FFFFFFFu) >> 5;
           if ((int)m[s] < 0) occ[w] = 0; else multi[w] = 0;
         }
