@@ -20,7 +20,8 @@ cudaError_t sw_extend_s32_launch(const SwParams &p, int sm_count, cudaStream_t s
 uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions, bool fast);
 bool search_uses_fast(uint32_t list_len, bool allow_fast);
 cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream, bool allow_fast);
-bool search_bucket_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions, uint32_t *tile_bits);
+bool search_bucket_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions, uint32_t *tile_bits,
+                      uint32_t *bucket_cap);
 int search_bucket_grid(int sm_count);
 cudaError_t seed_search_bucket_launch(const SearchParams &p, int sm_count, cudaStream_t stream);
 int search_max_list_len();
@@ -236,7 +237,6 @@ struct gm_context {
   uint32_t staging_cap = 1u << 15;
   DevBuf<uint16_t> buckets;           // bucket seed search: [grid][tiles][bucket_cap] marks
   DevBuf<uint32_t> fallback;          // queries the bucket kernel hands to the sweep kernel
-  uint32_t bucket_cap = 384;
   DevBuf<uint32_t> prefix;            // scan output (n_queries + 1)
   DevBuf<uint32_t> bounds;            // gm_candidates_pack part boundaries
   DevBuf<uint32_t> gather0, gather1, gather2;
@@ -568,16 +568,17 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     p.positions_visited = c->counters.p + 1;
     p.overflow = reinterpret_cast<int *>(c->small.p + 2);
     p.debug = getenv("GM_SEARCH_DEBUG") ? (uint32_t)atoi(getenv("GM_SEARCH_DEBUG")) : 0u;
-    uint32_t tile_bits = 0, launches = 1;
+    uint32_t tile_bits = 0, bucket_cap = 0, launches = 1;
     const bool bucket = c->search_bucket && c->search_fast &&
-                        search_bucket_ok(p.threshold, p.list_len, p.n_regions, &tile_bits);
+                        search_bucket_ok(p.threshold, p.list_len, p.n_regions, &tile_bits, &bucket_cap);
     if (bucket) {
       const uint32_t n_tiles = (p.n_regions + (1u << tile_bits) - 1) >> tile_bits;
       const int bgrid = search_bucket_grid(c->sm_count);
-      GM_CUDA(c->buckets.ensure((size_t)bgrid * n_tiles * c->bucket_cap));
+      GM_CUDA(c->buckets.ensure((size_t)bgrid * n_tiles * bucket_cap));
+      GM_CUDA(c->staging.ensure((size_t)bgrid * c->staging_cap));
       GM_CUDA(c->fallback.ensure(c->n_queries));
       p.tile_bits = tile_bits;
-      p.bucket_cap = c->bucket_cap;
+      p.bucket_cap = bucket_cap;
       p.buckets = c->buckets.p;
       p.fallback_list = c->fallback.p;
       p.fallback_n = c->small.p + 6;

@@ -647,12 +647,9 @@ __global__ void __launch_bounds__(kFastThreads, 2) seed_search_fast_kernel(const
 // Queries that do not fit the fixed capacities (a bucket, a tile's emit list, the staging area -
 // low-complexity queries against repetitive databases) are queued for the sweep kernel above,
 // which has no such limits; the results are identical either way.
-constexpr int kBkThreads = 384;
-constexpr int kBkWarps = kBkThreads / 32;
-constexpr int kBkMaxTiles = 512;
+constexpr int kBkMaxTiles = 1024;
 constexpr int kBkLists = 64;
-constexpr int kBkSlots = 8;             // register-resident marks per lane per tile
-constexpr int kBkUnroll = 4;            // chunks in flight per warp in phase A
+constexpr int kBkUnroll = 4;            // chunks per batch in phase A (two batches in flight)
 constexpr int kBkEmitCap = 126;         // emitted regions per tile (u16 list, 64 words with its counter)
 constexpr uint32_t kBkEmpty = 0x7FFFFFFFu;   // empty register slot: bit 31 (owner) clear, no valid region
 constexpr uint32_t kBkMaxTileBits = 15;
@@ -663,16 +660,19 @@ struct BucketShared {
   uint32_t pre[kBkLists + 1];             // exclusive prefix of chunks per list
   uint32_t cnt[kBkMaxTiles];              // marks per tile; phase C: output offset of the tile
   uint32_t tile_off[kBkMaxTiles];         // staging offset of the tile's candidates
-  uint32_t tile_cnt[kBkMaxTiles];
+  uint16_t tile_cnt[kBkMaxTiles];         // <= kBkEmitCap + 1
   uint32_t halo[kBkMaxTiles / 32 + 1];    // bit t: region 0 of tile t is occupied
-  uint32_t query, next_tile, stage_n, bad;
+  uint32_t query, stage_n, bad;
   unsigned long long base;
   unsigned long long visited;
 };
 
-__global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const SearchParams p) {
+// NW warps per CTA, SLOTS register-resident marks per lane per tile, MINB CTAs per SM.
+template <int NW, int SLOTS, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) seed_search_bucket_kernel(const SearchParams p) {
   extern __shared__ __align__(16) uint32_t dyn[];
   __shared__ BucketShared sh;
+  constexpr uint32_t kThreads = NW * 32;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t r = p.log_region, TB = p.tile_bits, xmask = (1u << TB) - 1u;
   const uint32_t W = 1u << (TB - 5);                     // words per private bitmap
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
   uint16_t *bucket = p.buckets + (size_t)blockIdx.x * n_tiles * S;
   uint32_t *stage = p.staging + (size_t)blockIdx.x * p.staging_cap;
 
-  for (uint32_t i = tid; i < kBkWarps * (2 * W + 1 + 64); i += kBkThreads) dyn[i] = 0;
+  for (uint32_t i = tid; i < NW * (2 * W + 1 + 64); i += kThreads) dyn[i] = 0;
   if (tid == 0) sh.visited = 0;
   __syncthreads();
 
@@ -707,9 +707,9 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
       sh.lend[j] = e;
       if (e > b) atomicAdd(&sh.visited, (unsigned long long)(e - b));
     }
-    for (uint32_t t = tid; t < n_tiles; t += kBkThreads) { sh.cnt[t] = 0; sh.tile_cnt[t] = 0; }
+    for (uint32_t t = tid; t < n_tiles; t += kThreads) { sh.cnt[t] = 0; sh.tile_cnt[t] = 0; }
     if (tid < kBkMaxTiles / 32 + 1) sh.halo[tid] = 0;
-    if (tid == 0) { sh.next_tile = 0; sh.stage_n = 0; sh.bad = 0; }
+    if (tid == 0) { sh.stage_n = 0; sh.bad = 0; }
     __syncthreads();
     if (warp == 0) {
       uint32_t carry = 0;
@@ -729,34 +729,55 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
     }
     __syncthreads();
 
-    // ---- phase A: marks -> tile buckets
-    for (uint32_t j = 0; j < p.list_len; ++j) {
-      const uint32_t b = sh.lbeg[j], e = sh.lend[j], off = j * p.shift;
-      const uint32_t nj = (e - b + 31) / 32;
-      // this warp's chunks of list j: global chunk number (pre[j] + c) % warps == warp
-      const uint32_t c0 = (warp + kBkWarps - sh.pre[j] % kBkWarps) % kBkWarps;
-      for (uint32_t c = c0; c < nj; c += kBkWarps * kBkUnroll) {
-        uint32_t pos[kBkUnroll], prev[kBkUnroll];
+    // ---- phase A: marks -> tile buckets.  The warp walks its batches (up to kBkUnroll chunks of
+    // one list) with the loads of the next batch in flight while it scatters the current one.
+    {
+      uint32_t j = 0, c = 0, lb = 0, le = 0, nj = 0;
+      auto seek = [&]() {   // first list >= j holding a chunk for this warp
+        while (j < p.list_len) {
+          lb = sh.lbeg[j];
+          le = sh.lend[j];
+          nj = (le - lb + 31) / 32;
+          c = (warp + NW - sh.pre[j] % NW) % NW;   // global chunk number (pre[j] + c) % NW == warp
+          if (c < nj) return;
+          ++j;
+        }
+      };
+      auto load = [&](uint32_t (&pos)[kBkUnroll], uint32_t (&prev)[kBkUnroll]) {
 #pragma unroll
         for (int u = 0; u < kBkUnroll; ++u) {
-          const uint32_t idx = b + 32u * (c + u * kBkWarps) + lane;
+          const uint32_t idx = lb + 32u * (c + u * NW) + lane;
           pos[u] = kNone;
           prev[u] = kNone;
-          if (idx < e) {
+          if (j < p.list_len && idx < le) {
             pos[u] = __ldg(p.positions + idx);
-            if (idx > b) prev[u] = __ldg(p.positions + idx - 1);
+            if (idx > lb) prev[u] = __ldg(p.positions + idx - 1);
           }
         }
+      };
+      seek();
+      uint32_t pos[kBkUnroll], prev[kBkUnroll];
+      load(pos, prev);
+      while (j < p.list_len) {
+        const uint32_t off = j * p.shift;
+        c += NW * kBkUnroll;
+        if (c >= nj) { ++j; seek(); }
+        uint32_t npos[kBkUnroll], nprev[kBkUnroll];
+        load(npos, nprev);
 #pragma unroll
         for (int u = 0; u < kBkUnroll; ++u) {
-          if (pos[u] == kNone) continue;
-          const uint32_t d = (pos[u] - off) >> r;
-          if (prev[u] != kNone && ((prev[u] - off) >> r) == d) continue;   // same list, same region
-          const uint32_t t = d >> TB, x = d & xmask;
-          const uint32_t slot = atomicAdd(&sh.cnt[t], 1u);
-          if (slot < S) bucket[t * S + slot] = (uint16_t)x;
-          else sh.bad = 1;
-          if (x == 0) atomicOr(&sh.halo[t >> 5], 1u << (t & 31));
+          if (pos[u] != kNone) {
+            const uint32_t d = (pos[u] - off) >> r;
+            if (prev[u] == kNone || ((prev[u] - off) >> r) != d) {   // first of its list in region d
+              const uint32_t t = d >> TB, x = d & xmask;
+              const uint32_t slot = atomicAdd(&sh.cnt[t], 1u);
+              if (slot < S) bucket[t * S + slot] = (uint16_t)x;
+              else sh.bad = 1;
+              if (x == 0) atomicOr(&sh.halo[t >> 5], 1u << (t & 31));
+            }
+          }
+          pos[u] = npos[u];
+          prev[u] = nprev[u];
         }
       }
     }
@@ -764,95 +785,110 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
     bool bad = sh.bad != 0;
 
     if (!bad) {
-      // ---- phase B: one warp per tile
-      while (true) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(&sh.next_tile, 1u);
-        t = __shfl_sync(kFull, t, 0);
-        if (t >= n_tiles) break;
-        const uint32_t n = sh.cnt[t];
-        if (n == 0) continue;
-        uint16_t *bk = bucket + t * S;
-        if (lane == 0)
-          occ[W] = (t + 1 < n_tiles) ? (sh.halo[(t + 1) >> 5] >> ((t + 1) & 31)) & 1u : 0u;
-        // arrive: the first mark at a region owns it (bit 31 of m), later ones flag it in `multi`
-        uint32_t m[kBkSlots];
+      // ---- phase B: one warp per tile (t = warp, warp + NW, ...), next tile's bucket prefetched
+      uint32_t t = warp;
+      uint32_t n = t < n_tiles ? sh.cnt[t] : 0u;
+      uint32_t xs[SLOTS];
 #pragma unroll
-        for (int s = 0; s < kBkSlots; ++s) {
+      for (int s = 0; s < SLOTS; ++s) {
+        const uint32_t i = s * 32 + lane;
+        xs[s] = (t < n_tiles && i < n) ? bucket[t * S + i] : 0xFFFFu;
+      }
+      while (t < n_tiles) {
+        const uint32_t tn = t + NW;
+        const uint32_t nn = tn < n_tiles ? sh.cnt[tn] : 0u;
+        uint32_t nxs[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
           const uint32_t i = s * 32 + lane;
-          m[s] = kBkEmpty;
-          if (i < n) {
+          nxs[s] = (tn < n_tiles && i < nn) ? bucket[tn * S + i] : 0xFFFFu;
+        }
+        if (n != 0) {
+          uint16_t *bk = bucket + t * S;
+          if (lane == 0)
+            occ[W] = (t + 1 < n_tiles) ? (sh.halo[(t + 1) >> 5] >> ((t + 1) & 31)) & 1u : 0u;
+          // arrive: the first mark at a region owns it (bit 31 of m), later ones flag it in `multi`
+          uint32_t m[SLOTS];
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+            m[s] = kBkEmpty;
+            if (xs[s] != 0xFFFFu) {
+              const uint32_t x = xs[s], bit = 1u << (x & 31);
+              const uint32_t old = atomicOr(&occ[x >> 5], bit);
+              m[s] = x;
+              if (old & bit) atomicOr(&multi[x >> 5], bit);
+              else m[s] = x | 0x80000000u;
+            }
+          }
+          for (uint32_t i = SLOTS * 32 + lane; i < n; i += 32) {   // beyond the register slots
             const uint32_t x = bk[i], bit = 1u << (x & 31);
             const uint32_t old = atomicOr(&occ[x >> 5], bit);
-            m[s] = x;
             if (old & bit) atomicOr(&multi[x >> 5], bit);
-            else m[s] = x | 0x80000000u;
+            else bk[i] = (uint16_t)(x | 0x8000u);                    // x < 2^15: bit 15 = owner
           }
-        }
-        for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) {   // beyond the register slots
-          const uint32_t x = bk[i], bit = 1u << (x & 31);
-          const uint32_t old = atomicOr(&occ[x >> 5], bit);
-          if (old & bit) atomicOr(&multi[x >> 5], bit);
-          else bk[i] = (uint16_t)(x | 0x8000u);                      // x < 2^15: bit 15 = owner
-        }
-        __syncwarp();
-        // decide: owners only; emitted regions go to the warp's emit list (unordered)
+          __syncwarp();
+          // decide: owners only; emitted regions go to the warp's emit list (unordered)
 #pragma unroll
-        for (int s = 0; s < kBkSlots; ++s) {
-          if ((int)m[s] >= 0) continue;                              // not an owner / empty slot
-          const uint32_t x = m[s] & 0x7FFFFFFFu, y = x + 1;
-          if (((multi[x >> 5] >> (x & 31)) | (occ[y >> 5] >> (y & 31))) & 1u) {
-            const uint32_t i = atomicAdd(elist_n, 1u);
-            if (i < kBkEmitCap) elist[i] = (uint16_t)x;
+          for (int s = 0; s < SLOTS; ++s) {
+            if ((int)m[s] >= 0) continue;                            // not an owner / empty slot
+            const uint32_t x = m[s] & 0x7FFFFFFFu, y = x + 1;
+            if (((multi[x >> 5] >> (x & 31)) | (occ[y >> 5] >> (y & 31))) & 1u) {
+              const uint32_t i = atomicAdd(elist_n, 1u);
+              if (i < kBkEmitCap) elist[i] = (uint16_t)x;
+            }
           }
-        }
-        for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) {
-          const uint32_t v = bk[i];
-          if (!(v & 0x8000u)) continue;
-          const uint32_t x = v & 0x7FFFu, y = x + 1;
-          if (((multi[x >> 5] >> (x & 31)) | (occ[y >> 5] >> (y & 31))) & 1u) {
-            const uint32_t k = atomicAdd(elist_n, 1u);
-            if (k < kBkEmitCap) elist[k] = (uint16_t)x;
+          for (uint32_t i = SLOTS * 32 + lane; i < n; i += 32) {
+            const uint32_t v = bk[i];
+            if (!(v & 0x8000u)) continue;
+            const uint32_t x = v & 0x7FFFu, y = x + 1;
+            if (((multi[x >> 5] >> (x & 31)) | (occ[y >> 5] >> (y & 31))) & 1u) {
+              const uint32_t k = atomicAdd(elist_n, 1u);
+              if (k < kBkEmitCap) elist[k] = (uint16_t)x;
+            }
           }
-        }
-        // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an unoccupied
-        // region 0 still emits when region 1 alone reaches the threshold.
-        const uint32_t virt = (t == 0 && !(occ[0] & 1u) && (multi[0] & 2u)) ? 1u : 0u;
-        __syncwarp();
-        // clear what this tile set
+          // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an
+          // unoccupied region 0 still emits when region 1 alone reaches the threshold.
+          const uint32_t virt = (t == 0 && !(occ[0] & 1u) && (multi[0] & 2u)) ? 1u : 0u;
+          __syncwarp();
+          // clear what this tile set
 #pragma unroll
-        for (int s = 0; s < kBkSlots; ++s) {
-          if (m[s] == kBkEmpty) continue;
-          const uint32_t w = (m[s] & 0x7FFFFFFFu) >> 5;
-          if ((int)m[s] < 0) occ[w] = 0; else multi[w] = 0;
-        }
-        for (uint32_t i = kBkSlots * 32 + lane; i < n; i += 32) {
-          const uint32_t v = bk[i], w = (v & 0x7FFFu) >> 5;
-          if (v & 0x8000u) occ[w] = 0; else multi[w] = 0;
-        }
-        const uint32_t k = *elist_n;
-        __syncwarp();
-        if (lane == 0) { occ[W] = 0; *elist_n = 0; }
-        if (k > kBkEmitCap) {
-          if (lane == 0) sh.bad = 1;
-        } else if (k + virt) {
-          // exactly one entry per emitted region: its rank is the number of smaller entries
-          uint32_t off = 0;
-          if (lane == 0) {
-            off = atomicAdd(&sh.stage_n, k + virt);
-            sh.tile_off[t] = off;
-            sh.tile_cnt[t] = k + virt;
+          for (int s = 0; s < SLOTS; ++s) {
+            if (m[s] == kBkEmpty) continue;
+            const uint32_t w = (m[s] & 0x7FFFFFFFu) >> 5;
+            if ((int)m[s] < 0) occ[w] = 0; else multi[w] = 0;
           }
-          off = __shfl_sync(kFull, off, 0);
-          if (virt && lane == 0 && off < p.staging_cap) stage[off] = 0;   // region 0 of tile 0
-          for (uint32_t i = lane; i < k; i += 32) {
-            const uint32_t x = elist[i];
-            uint32_t rank = virt;
-            for (uint32_t i2 = 0; i2 < k; ++i2) rank += elist[i2] < x;
-            if (off + rank < p.staging_cap) stage[off + rank] = ((t << TB) + x) << r;
+          for (uint32_t i = SLOTS * 32 + lane; i < n; i += 32) {
+            const uint32_t v = bk[i], w = (v & 0x7FFFu) >> 5;
+            if (v & 0x8000u) occ[w] = 0; else multi[w] = 0;
           }
+          const uint32_t k = *elist_n;
+          __syncwarp();
+          if (lane == 0) { occ[W] = 0; *elist_n = 0; }
+          if (k > kBkEmitCap) {
+            if (lane == 0) sh.bad = 1;
+          } else if (k + virt) {
+            // exactly one entry per emitted region: its rank is the number of smaller entries
+            uint32_t off = 0;
+            if (lane == 0) {
+              off = atomicAdd(&sh.stage_n, k + virt);
+              sh.tile_off[t] = off;
+              sh.tile_cnt[t] = (uint16_t)(k + virt);
+            }
+            off = __shfl_sync(kFull, off, 0);
+            if (virt && lane == 0 && off < p.staging_cap) stage[off] = 0;   // region 0 of tile 0
+            for (uint32_t i = lane; i < k; i += 32) {
+              const uint32_t x = elist[i];
+              uint32_t rank = virt;
+              for (uint32_t i2 = 0; i2 < k; ++i2) rank += elist[i2] < x;
+              if (off + rank < p.staging_cap) stage[off + rank] = ((t << TB) + x) << r;
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        t = tn;
+        n = nn;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) xs[s] = nxs[s];
       }
       __syncthreads();
       bad = sh.bad != 0 || sh.stage_n > p.staging_cap;
@@ -894,7 +930,7 @@ __global__ void __launch_bounds__(kBkThreads, 2) seed_search_bucket_kernel(const
     __syncthreads();
     const unsigned long long cbase = sh.base;
     if (n && cbase + n <= p.cand_capacity) {
-      for (uint32_t t = warp; t < n_tiles; t += kBkWarps) {
+      for (uint32_t t = warp; t < n_tiles; t += NW) {
         const uint32_t c = sh.tile_cnt[t], src = sh.tile_off[t], dst = sh.cnt[t];
         for (uint32_t i = lane; i < c; i += 32) p.cand_start[cbase + dst + i] = stage[src + i];
       }
@@ -960,28 +996,62 @@ cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t str
 }
 
 // ---- bucket path configuration
-bool search_bucket_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions, uint32_t *tile_bits) {
+struct BucketConfig { int nw, slots, minb; uint32_t tile_bits, bucket_cap; };
+
+// Tiles of about 2 * 32 * slots marks for the expected mark density (~ list_len * interval length
+// per query); GM_BUCKET_CFG="nw,slots,max_tile_bits" overrides the default for tuning runs.
+static BucketConfig bucket_config(uint32_t n_regions) {
+  BucketConfig c = {8, 4, 4, 14, 192};
+  if (const char *env = getenv("GM_BUCKET_CFG")) {
+    int nw = 0, slots = 0, tb = 0;
+    if (sscanf(env, "%d,%d,%d", &nw, &slots, &tb) == 3) {
+      c.nw = nw; c.slots = slots; c.tile_bits = (uint32_t)tb;
+      c.bucket_cap = slots >= 8 ? 384 : 192;
+    }
+  }
+  uint32_t tb = kBkMinTileBits;
+  const uint32_t want_tiles = c.tile_bits >= 15 ? 256 : 512;
+  while (tb < c.tile_bits && ((n_regions + (1u << tb) - 1) >> tb) > want_tiles) ++tb;
+  c.tile_bits = tb;
+  return c;
+}
+
+bool search_bucket_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions, uint32_t *tile_bits,
+                      uint32_t *bucket_cap) {
   if (threshold != 2 || list_len > kBkLists) return false;
-  uint32_t tb = kBkMinTileBits;     // about 256 tiles, 2^10 .. 2^15 regions each
-  while (tb < kBkMaxTileBits && ((n_regions + (1u << tb) - 1) >> tb) > 256) ++tb;
-  if (((n_regions + (1u << tb) - 1) >> tb) > kBkMaxTiles) return false;
-  *tile_bits = tb;
+  const BucketConfig c = bucket_config(n_regions);
+  if (((n_regions + (1u << c.tile_bits) - 1) >> c.tile_bits) > kBkMaxTiles) return false;
+  *tile_bits = c.tile_bits;
+  *bucket_cap = c.bucket_cap;
   return true;
 }
 
-size_t search_bucket_smem(uint32_t tile_bits) {
-  return (size_t)kBkWarps * (2 * (1u << (tile_bits - 5)) + 1 + 64) * sizeof(uint32_t);
+int search_bucket_grid(int sm_count) { return sm_count * 6; }   // upper bound for the scratch size
+
+template <int NW, int SLOTS, int MINB>
+static cudaError_t bucket_launch(const SearchParams &p, int sm_count, cudaStream_t stream) {
+  const size_t smem = (size_t)NW * (2 * (1u << (p.tile_bits - 5)) + 1 + 64) * sizeof(uint32_t);
+  auto kern = seed_search_bucket_kernel<NW, SLOTS, MINB>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  int per_sm = 0;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  if (per_sm > 6) per_sm = 6;
+  kern<<<sm_count * per_sm, NW * 32, smem, stream>>>(p);
+  return cudaGetLastError();
 }
 
-int search_bucket_grid(int sm_count) { return sm_count * 2; }
-
 cudaError_t seed_search_bucket_launch(const SearchParams &p, int sm_count, cudaStream_t stream) {
-  const size_t smem = search_bucket_smem(p.tile_bits);
-  cudaError_t err = cudaFuncSetAttribute(seed_search_bucket_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) return err;
-  seed_search_bucket_kernel<<<search_bucket_grid(sm_count), kBkThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  const BucketConfig c = bucket_config(p.n_regions);
+  if (c.nw == 12 && c.slots == 8) return bucket_launch<12, 8, 2>(p, sm_count, stream);
+  if (c.nw == 12 && c.slots == 4) return bucket_launch<12, 4, 3>(p, sm_count, stream);
+  if (c.nw == 8 && c.slots == 8) return bucket_launch<8, 8, 3>(p, sm_count, stream);
+  if (c.nw == 8 && c.slots == 4) return bucket_launch<8, 4, 4>(p, sm_count, stream);
+  if (c.nw == 4 && c.slots == 4) return bucket_launch<4, 4, 8>(p, sm_count, stream);
+  if (c.nw == 16 && c.slots == 4) return bucket_launch<16, 4, 2>(p, sm_count, stream);
+  return cudaErrorInvalidValue;
 }
 
 int search_max_list_len() { return kMaxListLen; }
