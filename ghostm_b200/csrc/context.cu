@@ -576,6 +576,7 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
       const int bgrid = search_bucket_grid(c->sm_count);
       GM_CUDA(c->buckets.ensure((size_t)bgrid * n_tiles * bucket_cap));
       GM_CUDA(c->staging.ensure((size_t)bgrid * c->staging_cap));
+      p.staging = c->staging.p;   // ensure() may have moved it
       GM_CUDA(c->fallback.ensure(c->n_queries));
       p.tile_bits = tile_bits;
       p.bucket_cap = bucket_cap;
