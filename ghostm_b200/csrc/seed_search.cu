@@ -1001,12 +1001,12 @@ struct BucketConfig { int nw, slots, minb; uint32_t tile_bits, bucket_cap; };
 // Tiles of about 2 * 32 * slots marks for the expected mark density (~ list_len * interval length
 // per query); GM_BUCKET_CFG="nw,slots,max_tile_bits" overrides the default for tuning runs.
 static BucketConfig bucket_config(uint32_t n_regions) {
-  BucketConfig c = {8, 4, 4, 14, 192};
+  BucketConfig c = {12, 4, 3, 14, 384};
   if (const char *env = getenv("GM_BUCKET_CFG")) {
     int nw = 0, slots = 0, tb = 0;
     if (sscanf(env, "%d,%d,%d", &nw, &slots, &tb) == 3) {
       c.nw = nw; c.slots = slots; c.tile_bits = (uint32_t)tb;
-      c.bucket_cap = slots >= 8 ? 384 : 192;
+      c.bucket_cap = 384;
     }
   }
   uint32_t tb = kBkMinTileBits;
