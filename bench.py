@@ -224,8 +224,11 @@ def run_ours(a):
     stream = torch.cuda.ExternalStream(ctx.stream())
     stream_end = torch.cuda.ExternalStream(back_ctx.stream()) if sharded else stream
 
+    host_t = {}
+
     def step(s: int, e2e: bool):
         b = s % n_batches
+        t_0 = time.perf_counter()
         if not sharded:
             if e2e:
                 ctx.query_upload_ptr(q_pinned[b].data_ptr(), a.queries, a.length)
@@ -241,10 +244,13 @@ def run_ours(a):
             back_ctx.query_upload_ptr(q_pinned[b][base:stop].data_ptr(), stop - base, a.length)
         else:
             back_ctx.results_clear()
+        host_t["upload"] = host_t.get("upload", 0.0) + time.perf_counter() - t_0
         shard.shard_step(front, back, dist, rank, world, n_chunks, bounds,
-                         before_back=torch.cuda.synchronize)
+                         before_back=torch.cuda.synchronize, timers=host_t)
+        t_1 = time.perf_counter()
         if e2e:
             back_ctx.results_download_ptr(hits_pinned.data_ptr(), counts_pinned.data_ptr())
+        host_t["download"] = host_t.get("download", 0.0) + time.perf_counter() - t_1
 
     def barrier():
         torch.cuda.synchronize()
@@ -264,6 +270,7 @@ def run_ours(a):
             C.memset(C.byref(st_), 0, C.sizeof(st_))
         if sharded:
             front.launches = back.launches = 0
+        host_t.clear()
         sampler = ClockSampler(local) if rank == 0 else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -287,10 +294,11 @@ def run_ours(a):
         st = stats.as_dict()
         for k in ("ms_merge", "ms_traceback", "tracebacks", "candidate_chunks"):
             st[k] += getattr(stats_back, k)
+        st["host_ms_per_step"] = {k: round(v * 1e3 / a.steps, 3) for k, v in host_t.items()}
         return t.tolist(), cells.tolist(), st, clocks
 
     (dev_ms, wall_ms), (cells, cands, launches, positions), st, clocks = timed(False)
-    (e_dev_ms, e_wall_ms), (e_cells, _, _, _), _, _ = timed(True)
+    (e_dev_ms, e_wall_ms), (e_cells, _, _, _), e_st, _ = timed(True)
 
     out = None
     if rank == 0:
@@ -351,6 +359,9 @@ def run_ours(a):
                                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             "stage_ms_per_step_rank0": {k: st[k] / a.steps for k in
                                         ("ms_search", "ms_score", "ms_merge", "ms_traceback")},
+            "host_ms_per_step_rank0": st.get("host_ms_per_step"),
+            "wall_ms_per_step": wall_ms / a.steps,
+            "e2e_host_ms_per_step_rank0": e_st.get("host_ms_per_step"),
             "setup_s": setup_s,
         }
         if world == 1 and not a.no_cpu_baseline:

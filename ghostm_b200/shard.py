@@ -178,24 +178,38 @@ def front_round(front: Front, chunk_id: int, n_chunks: int, bounds: np.ndarray):
 
 
 def shard_step(front: Front, back: Back, dist, rank: int, world: int, n_chunks: int,
-               bounds: np.ndarray, before_back=None) -> None:
+               bounds: np.ndarray, before_back=None, timers=None) -> None:
     """One query batch on this rank: per round of `world` chunks search + extend the owned
     chunk, exchange by query slice, merge the round's chunks into the own slice; finally
     TraceBack of the survivors.  `dist` is torch.distributed (unused when world == 1);
-    `before_back`, if given, is called after every exchange (e.g. a stream synchronisation)."""
+    `before_back`, if given, is called after every exchange (e.g. a stream synchronisation);
+    `timers`, if a dict, accumulates host wall seconds per phase (front / exchange / back)."""
+    import time
     base, stop = int(bounds[rank]), int(bounds[rank + 1])
+
+    def lap(key, t0):
+        if timers is not None:
+            timers[key] = timers.get(key, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     for round0 in range(0, n_chunks, world):
+        t0 = time.perf_counter()
         counts, data, totals, segs = front_round(front, round0 + rank, n_chunks, bounds)
+        t0 = lap("front", t0)
         if world == 1:
             inbox = [(counts, data, int(totals[0]), segs)]
         else:
             inbox = exchange(dist, rank, world, bounds, counts, data, totals, segs)
         if before_back is not None:
             before_back()
+        t0 = lap("exchange", t0)
         if stop > base:
             back_round(back, inbox, round0, n_chunks, base, stop)
+        t0 = lap("back", t0)
+    t0 = time.perf_counter()
     if stop > base:
         back.finish()
+    lap("back", t0)
 
 
 # ---- engines over the C ABI (GPU) ----------------------------------------------------------
