@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--queries", type=int, default=16384, help="queries per step (batch)")
+    ap.add_argument("--queries", type=int, default=65536, help="queries per step (batch)")
     ap.add_argument("--length", type=int, default=75)
     ap.add_argument("--db-residues", type=float, default=1e9)
     ap.add_argument("--chunk-mib", type=float, default=120.0)
