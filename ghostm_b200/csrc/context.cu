@@ -23,6 +23,8 @@ cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t str
 bool search_bucket_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions, uint32_t *tile_bits,
                       uint32_t *bucket_cap);
 int search_bucket_grid(int sm_count);
+bool search_hash_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions);
+cudaError_t seed_search_hash_launch(const SearchParams &p, int sm_count, cudaStream_t stream);
 cudaError_t seed_search_bucket_launch(const SearchParams &p, int sm_count, cudaStream_t stream);
 int search_max_list_len();
 int search_max_threshold();
@@ -259,6 +261,7 @@ struct gm_context {
   bool chunk_tab_dirty = true;
   bool search_fast = true;   // balanced register-resident search kernel when the options allow it
   bool search_bucket = true; // bucket kernel (threshold 2) in front of it
+  bool search_hash = true;   // hash kernel (threshold 2) in front of both
   bool traceback_fast = true;
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits
@@ -569,8 +572,15 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     p.overflow = reinterpret_cast<int *>(c->small.p + 2);
     p.debug = getenv("GM_SEARCH_DEBUG") ? (uint32_t)atoi(getenv("GM_SEARCH_DEBUG")) : 0u;
     uint32_t tile_bits = 0, bucket_cap = 0, launches = 1;
-    const bool bucket = c->search_bucket && c->search_fast &&
+    const bool hash = c->search_hash && c->search_fast &&
+                      search_hash_ok(p.threshold, p.list_len, p.n_regions);
+    const bool bucket = !hash && c->search_bucket && c->search_fast &&
                         search_bucket_ok(p.threshold, p.list_len, p.n_regions, &tile_bits, &bucket_cap);
+    if (hash) {
+      GM_CUDA(c->fallback.ensure(c->n_queries));
+      p.fallback_list = c->fallback.p;
+      p.fallback_n = c->small.p + 6;
+    }
     if (bucket) {
       const uint32_t n_tiles = (p.n_regions + (1u << tile_bits) - 1) >> tile_bits;
       const int bgrid = search_bucket_grid(c->sm_count);
@@ -585,8 +595,9 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
       p.fallback_n = c->small.p + 6;
     }
     GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    if (bucket) {
-      GM_CUDA(seed_search_bucket_launch(p, c->sm_count, c->stream));
+    if (bucket || hash) {
+      if (hash) GM_CUDA(seed_search_hash_launch(p, c->sm_count, c->stream));
+      else GM_CUDA(seed_search_bucket_launch(p, c->sm_count, c->stream));
       uint32_t n_fb = 0;
       GM_CUDA(cudaMemcpyAsync(&n_fb, c->small.p + 6, 4, cudaMemcpyDeviceToHost, c->stream));
       GM_CUDA(cudaStreamSynchronize(c->stream));
@@ -904,6 +915,7 @@ extern "C" int gm_set_search_variant(gm_context *c, int fast) {
   if (int r = check_ctx(c)) return r;
   c->search_fast = fast != 0;
   c->search_bucket = fast >= 2;
+  c->search_hash = fast >= 3;
   c->traceback_fast = fast != 0;
   return 0;
 }

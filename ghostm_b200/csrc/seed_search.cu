@@ -939,6 +939,303 @@ __global__ void __launch_bounds__(NW * 32, MINB) seed_search_bucket_kernel(const
   if (tid == 0 && sh.visited) atomicAdd(p.positions_visited, sh.visited);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Hash path (threshold 2, list_len <= 64): no tiles at all.  Per query, one CTA of 32 warps:
+//   pass 1  stream all positions (32-position chunks dealt to the warps through a chunk->list
+//           table); every MARK (first position of its list in a region d) sets bit d mod 2^20 of a
+//           FOLDED occupancy bitmap (128 KB); a mark that finds its bit set also sets the coarse
+//           collision bitmap (one bit per 8 folded bits, 16 KB);
+//   pass 2  stream the same positions again (L2 hits): a mark is a SUSPECT iff its collision bit
+//           or one of its two neighbour bits in the folded bitmap is set.  Every mark that takes
+//           part in an emission is a suspect: two marks of one region collide, a mark of region d
+//           and one of d+1 are each other's neighbours; aliases of the fold only add false
+//           suspects (~14 % of the marks).  Suspects are appended with their exact region;
+//   pass 3  the bitmaps are cleared and their space becomes an open-addressing hash set of the
+//           suspects' exact regions: the first inserter of a region owns it, later ones flag it;
+//   pass 4  every owner emits its region d iff it is flagged (two lists) or d+1 is in the set
+//           (threshold 2: cnt(d) + cnt(d+1) >= 2, cnt(d) >= 1), plus the reference's virtual
+//           region 0 (aligner.cpp:451,483-494).  Emitted regions go to 32 range buckets
+//           (monotone in d), one warp ranks each bucket by counting: ascending output.
+// Everything is exact; the fold only decides how many suspects there are.  Queries that exceed
+// a capacity (chunk table, suspect list, a range bucket) are queued for the sweep kernel.
+constexpr int kHsThreads = 1024;
+constexpr int kHsWarps = kHsThreads / 32;
+constexpr uint32_t kHsOccBits = 1u << 20;
+constexpr uint32_t kHsOccWords = kHsOccBits / 32;       // 32768 words = 128 KB; later the hash set
+constexpr uint32_t kHsCollWords = kHsOccWords / 8;      // 4096 words = 16 KB; later the range buckets
+constexpr uint32_t kHsSuspCap = 16384;                  // 64 KB
+constexpr uint32_t kHsBuckets = 32;
+constexpr uint32_t kHsBucketCap = kHsCollWords / kHsBuckets;   // 128 emitted regions per bucket
+constexpr int kHsMaxChunks = 4096;
+constexpr int kHsUnroll = 4;
+constexpr size_t kHsSmemBytes = (size_t)(kHsOccWords + kHsCollWords + kHsSuspCap) * 4;
+
+struct HashShared {
+  uint32_t lbeg[kBkLists], lend[kBkLists];
+  uint32_t pre[kBkLists + 1];
+  uint8_t chunk_list[kHsMaxChunks];
+  uint32_t bcnt[kHsBuckets], boff[kHsBuckets + 1];
+  uint32_t query, n_susp, bad;
+  unsigned long long base;
+  unsigned long long visited;
+};
+
+__device__ __forceinline__ uint32_t hs_slot(uint32_t d) { return (d * 2654435761u) >> 17; }   // 15 bits
+
+// region d present in the hash set?  (*flagged: inserted more than once)
+__device__ __forceinline__ bool hs_find(const uint32_t *set, uint32_t d, bool *flagged) {
+  uint32_t s = hs_slot(d);
+  while (true) {
+    const uint32_t v = set[s];
+    if (v == 0) return false;
+    if ((v & 0x7FFFFFFFu) == d + 1) { *flagged = (v >> 31) != 0; return true; }
+    s = (s + 1) & (kHsOccWords - 1);
+  }
+}
+
+__global__ void __launch_bounds__(kHsThreads, 1) seed_search_hash_kernel(const SearchParams p) {
+  extern __shared__ __align__(16) uint32_t dyn[];
+  __shared__ HashShared sh;
+  uint32_t *occ = dyn;                       // [kHsOccWords]   passes 1-2: folded bitmap; 3-4: hash set
+  uint32_t *coll = dyn + kHsOccWords;        // [kHsCollWords]  passes 1-2: collisions; 4: range buckets
+  uint32_t *susp = coll + kHsCollWords;      // [kHsSuspCap]
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t r = p.log_region, hmask = kHsOccBits - 1;
+  const uint32_t lt = (1u << lane) - 1u;
+  // range bucket of a region: monotone in d, 32 buckets over [0, n_regions)
+  uint32_t bshift = 0;
+  while ((p.n_regions >> bshift) > kHsBuckets) ++bshift;
+  if ((p.n_regions >> bshift) == kHsBuckets) ++bshift;    // d < n_regions  =>  d >> bshift < 32
+
+  for (uint32_t i = tid; i < kHsOccWords + kHsCollWords; i += kHsThreads) dyn[i] = 0;
+  if (tid == 0) sh.visited = 0;
+  __syncthreads();
+
+  while (true) {
+    if (tid == 0) sh.query = atomicAdd(p.query_counter, 1u);
+    __syncthreads();
+    const uint32_t q = sh.query;
+    if (q >= p.n_queries) break;
+    const uint8_t *query = p.queries + (size_t)q * p.query_len;
+
+    // ---- phase 0: intervals (index.h:105-114), chunk prefix and chunk -> list table
+    if (tid < p.list_len) {
+      const uint32_t j = tid, off = j * p.shift;
+      const uint32_t key = get_key(query + off, p.seed);
+      uint32_t b = p.keys_count[key];
+      const uint32_t e = p.keys_count[key + 1];
+      while (b < e && p.positions[b] < off) ++b;                      // aligner.cpp:430-431
+      sh.lbeg[j] = b;
+      sh.lend[j] = e;
+      if (e > b) atomicAdd(&sh.visited, (unsigned long long)(e - b));
+    }
+    if (tid < kHsBuckets) sh.bcnt[tid] = 0;
+    if (tid == 0) { sh.n_susp = 0; sh.bad = 0; }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t carry = 0;
+      for (uint32_t j0 = 0; j0 < p.list_len; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const uint32_t c = j < p.list_len ? (sh.lend[j] - sh.lbeg[j] + 31) / 32 : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (j < p.list_len) sh.pre[j] = carry + incl - c;
+        carry += __shfl_sync(kFull, incl, 31);
+      }
+      if (lane == 0) sh.pre[p.list_len] = carry;
+    }
+    __syncthreads();
+    const uint32_t C = sh.pre[p.list_len];
+    bool bad = C > kHsMaxChunks;
+    if (!bad) {
+      for (uint32_t k = tid; k < C; k += kHsThreads) {
+        uint32_t lo = 0, hi = p.list_len;      // pre[lo] <= k < pre[hi]
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (sh.pre[mid] <= k) lo = mid; else hi = mid;
+        }
+        sh.chunk_list[k] = (uint8_t)lo;
+      }
+      __syncthreads();
+
+      // ---- passes 1 and 2 over the same chunks
+      for (int pass = 1; pass <= 2; ++pass) {
+        for (uint32_t k0 = warp; k0 < C; k0 += kHsWarps * kHsUnroll) {
+          uint32_t pos[kHsUnroll], prev0[kHsUnroll], offs[kHsUnroll];
+          bool firstpos[kHsUnroll];
+#pragma unroll
+          for (int u = 0; u < kHsUnroll; ++u) {
+            const uint32_t k = k0 + u * kHsWarps;
+            pos[u] = kNone;
+            prev0[u] = kNone;
+            offs[u] = 0;
+            firstpos[u] = false;
+            if (k < C) {
+              const uint32_t j = sh.chunk_list[k];
+              const uint32_t b = sh.lbeg[j];
+              const uint32_t idx = b + 32u * (k - sh.pre[j]) + lane;
+              offs[u] = j * p.shift;
+              firstpos[u] = idx == b;
+              if (idx < sh.lend[j]) {
+                pos[u] = __ldg(p.positions + idx);
+                if (lane == 0 && idx > b) prev0[u] = __ldg(p.positions + idx - 1);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kHsUnroll; ++u) {
+            const uint32_t k = k0 + u * kHsWarps;
+            if (k >= C) break;                                   // warp-uniform
+            const bool valid = pos[u] != kNone;
+            const uint32_t d = (pos[u] - offs[u]) >> r;
+            uint32_t pv = __shfl_up_sync(kFull, pos[u], 1);
+            if (lane == 0) pv = prev0[u];
+            // first position of its list in region d: no predecessor, or predecessor elsewhere
+            const bool mark = valid && (firstpos[u] || pv == kNone || ((pv - offs[u]) >> r) != d);
+            const uint32_t h = d & hmask;
+            if (pass == 1) {
+              if (mark) {
+                const uint32_t bit = 1u << (h & 31);
+                const uint32_t old = atomicOr(&occ[h >> 5], bit);
+                if (old & bit) atomicOr(&coll[h >> 8], 1u << ((h >> 3) & 31));
+              }
+            } else {
+              bool s = false;
+              if (mark) {
+                const uint32_t hl = (h - 1) & hmask, hr = (h + 1) & hmask;
+                s = (((occ[hl >> 5] >> (hl & 31)) | (occ[hr >> 5] >> (hr & 31)) |
+                      (coll[h >> 8] >> ((h >> 3) & 31))) & 1u) != 0;
+              }
+              const uint32_t bal = __ballot_sync(kFull, s);
+              if (bal) {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(&sh.n_susp, (uint32_t)__popc(bal));
+                at = __shfl_sync(kFull, at, 0);
+                if (s) {
+                  const uint32_t i = at + __popc(bal & lt);
+                  if (i < kHsSuspCap) susp[i] = d;
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      bad = sh.n_susp > kHsSuspCap;
+    }
+
+    // ---- the bitmaps are done: clear them (also on the bad path), their space is reused
+    {
+      uint4 *z = reinterpret_cast<uint4 *>(dyn);
+      for (uint32_t i = tid; i < (kHsOccWords + kHsCollWords) / 4; i += kHsThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    const uint32_t n_susp = sh.n_susp;
+    if (!bad) {
+      // ---- pass 3: hash set of the suspects' regions; bit 31 of susp[i] = owner of its region
+      for (uint32_t i = tid; i < n_susp; i += kHsThreads) {
+        const uint32_t d = susp[i];
+        uint32_t s = hs_slot(d);
+        while (true) {
+          const uint32_t cur = atomicCAS(&occ[s], 0u, d + 1);
+          if (cur == 0) { susp[i] = d | 0x80000000u; break; }
+          if ((cur & 0x7FFFFFFFu) == d + 1) { atomicOr(&occ[s], 0x80000000u); break; }
+          s = (s + 1) & (kHsOccWords - 1);
+        }
+      }
+      __syncthreads();
+      // ---- pass 4: owners decide; emitted regions into 32 range buckets
+      for (uint32_t i = tid; i < n_susp + 1; i += kHsThreads) {
+        uint32_t d;
+        bool emit;
+        if (i < n_susp) {
+          const uint32_t v = susp[i];
+          if (!(v >> 31)) continue;
+          d = v & 0x7FFFFFFFu;
+          bool flagged = false, f2 = false;
+          hs_find(occ, d, &flagged);
+          emit = flagged || hs_find(occ, d + 1, &f2);
+        } else {
+          // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an unoccupied
+          // region 0 still emits when region 1 alone reaches the threshold.
+          bool f0 = false, f1 = false;
+          d = 0;
+          emit = !hs_find(occ, 0, &f0) && hs_find(occ, 1, &f1) && f1;
+        }
+        if (emit) {
+          const uint32_t bk = d >> bshift;
+          const uint32_t at = atomicAdd(&sh.bcnt[bk], 1u);
+          if (at < kHsBucketCap) coll[bk * kHsBucketCap + at] = d;
+          else sh.bad = 1;
+        }
+      }
+      __syncthreads();
+      bad = sh.bad != 0;
+    }
+    // ---- clear the hash set for the next query
+    {
+      uint4 *z = reinterpret_cast<uint4 *>(occ);
+      for (uint32_t i = tid; i < kHsOccWords / 4; i += kHsThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (bad) {
+      if (tid < kHsBuckets) {   // bucket storage back to zero
+        const uint32_t c = min(sh.bcnt[tid], kHsBucketCap);
+        for (uint32_t i = 0; i < c; ++i) coll[tid * kHsBucketCap + i] = 0;
+      }
+      if (tid == 0) {
+        p.fallback_list[atomicAdd(p.fallback_n, 1u)] = q;
+        p.cand_off[q] = 0;
+        p.cand_cnt[q] = 0;
+      }
+      __syncthreads();
+      continue;
+    }
+    // ---- output: bucket offsets, global slice, ranks inside each bucket (one warp per bucket)
+    if (warp == 0) {
+      const uint32_t c = sh.bcnt[lane];
+      uint32_t incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+      }
+      sh.boff[lane] = incl - c;
+      if (lane == 31) {
+        const uint32_t n = incl;
+        sh.boff[32] = n;
+        sh.base = n ? atomicAdd(p.cand_cursor, (unsigned long long)n) : 0ull;
+        const bool fits = sh.base + n <= p.cand_capacity;
+        if (n && !fits) atomicExch(p.overflow, 1);
+        p.cand_off[q] = (uint32_t)sh.base;
+        p.cand_cnt[q] = fits ? n : 0u;
+      }
+    }
+    __syncthreads();
+    {
+      const uint32_t n = sh.boff[32];
+      const unsigned long long cbase = sh.base;
+      const bool fits = cbase + n <= p.cand_capacity;
+      const uint32_t c = sh.bcnt[warp];
+      uint32_t *bk = coll + warp * kHsBucketCap;
+      for (uint32_t i = lane; i < c; i += 32) {
+        const uint32_t d = bk[i];
+        uint32_t rank = 0;
+        for (uint32_t i2 = 0; i2 < c; ++i2) rank += bk[i2] < d;      // regions are distinct
+        if (fits) p.cand_start[cbase + sh.boff[warp] + rank] = d << r;
+      }
+      __syncwarp();
+      for (uint32_t i = lane; i < c; i += 32) bk[i] = 0;
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && sh.visited) atomicAdd(p.positions_visited, sh.visited);
+}
+
 // Generic dynamic shared memory size for a tile of M regions.
 size_t search_smem_bytes(int planes, uint32_t M) {   // count planes + the emit bitmap + summary
   const uint32_t words = M / 32 + 1;
@@ -1052,6 +1349,18 @@ cudaError_t seed_search_bucket_launch(const SearchParams &p, int sm_count, cudaS
   if (c.nw == 4 && c.slots == 4) return bucket_launch<4, 4, 8>(p, sm_count, stream);
   if (c.nw == 16 && c.slots == 4) return bucket_launch<16, 4, 2>(p, sm_count, stream);
   return cudaErrorInvalidValue;
+}
+
+bool search_hash_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions) {
+  return threshold == 2 && list_len <= kBkLists && n_regions <= (1u << 27);
+}
+
+cudaError_t seed_search_hash_launch(const SearchParams &p, int sm_count, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(seed_search_hash_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHsSmemBytes);
+  if (err != cudaSuccess) return err;
+  seed_search_hash_kernel<<<sm_count, kHsThreads, kHsSmemBytes, stream>>>(p);
+  return cudaGetLastError();
 }
 
 int search_max_list_len() { return kMaxListLen; }

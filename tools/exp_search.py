@@ -1,4 +1,4 @@
-"""Seed-search kernel timing on one GPU: bucket (2) vs sweep (1) kernel on a config-3 chunk, with a
+"""Seed-search kernel timing on one GPU: hash (3) vs bucket (2) vs sweep (1) kernel on a config-3 chunk, with a
 candidate-for-candidate comparison between the two."""
 import os, sys, json
 import numpy as np
@@ -13,7 +13,7 @@ ctx.db_build_index(0, seq, starts, 0xF)
 q = workloads.synth_queries(2, seq[:4 << 20].copy(), n_q, 75)
 ctx.query_upload(q)
 ref = None
-for variant in (2, 1):
+for variant in (3, 2, 1):
     ctx.set_search_variant(variant)
     best = 1e9
     for rep in range(4):
