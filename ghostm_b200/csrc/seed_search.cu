@@ -993,6 +993,62 @@ __device__ __forceinline__ bool hs_find(const uint32_t *set, uint32_t d, bool *f
   }
 }
 
+// One streaming pass over the query's positions.  Branch-free chunk addressing: chunk k of the
+// warp's round (clamped to the last chunk when the round runs past the end) -> list j, first index;
+// lane 0 also fetches the predecessor of the chunk's first position, the other lanes get theirs
+// from the left neighbour, so "first position of my list in region d" is one compare.
+template <int PASS>
+__device__ __forceinline__ void hs_stream(const SearchParams &p, HashShared &sh, uint32_t *occ,
+                                          uint32_t *coll, uint32_t *susp, uint32_t C, uint32_t warp,
+                                          uint32_t lane) {
+  const uint32_t r = p.log_region, hmask = kHsOccBits - 1, lt = (1u << lane) - 1u;
+  for (uint32_t k0 = warp; k0 < C; k0 += kHsWarps * kHsUnroll) {
+    uint32_t pos[kHsUnroll], prev0[kHsUnroll], offs[kHsUnroll];
+#pragma unroll
+    for (int u = 0; u < kHsUnroll; ++u) {
+      const uint32_t k = k0 + u * kHsWarps;
+      const uint32_t kc = k < C ? k : C - 1;
+      const uint32_t j = sh.chunk_list[kc];
+      const uint32_t b = sh.lbeg[j];
+      const uint32_t idx = b + 32u * (kc - sh.pre[j]) + lane;
+      const bool ok = k < C && idx < sh.lend[j];
+      offs[u] = j * p.shift;
+      pos[u] = ok ? __ldg(p.positions + idx) : kNone;
+      prev0[u] = (ok && lane == 0 && idx > b) ? __ldg(p.positions + idx - 1) : kNone;
+    }
+#pragma unroll
+    for (int u = 0; u < kHsUnroll; ++u) {
+      const uint32_t d = (pos[u] - offs[u]) >> r;
+      uint32_t pv = __shfl_up_sync(kFull, pos[u], 1);
+      if (lane == 0) pv = prev0[u];
+      // a valid lane > 0 always has a valid left neighbour of the same list; pv == kNone only for
+      // the very first position of the list
+      const bool mark = pos[u] != kNone && (pv == kNone || ((pv - offs[u]) >> r) != d);
+      const uint32_t h = d & hmask;
+      if (PASS == 1) {
+        if (mark) {
+          const uint32_t bit = 1u << (h & 31);
+          const uint32_t old = atomicOr(&occ[h >> 5], bit);
+          if (old & bit) atomicOr(&coll[h >> 8], 1u << ((h >> 3) & 31));
+        }
+      } else {
+        const uint32_t hl = (h - 1) & hmask, hr = (h + 1) & hmask;
+        const uint32_t t = ((occ[hl >> 5] >> (hl & 31)) | (occ[hr >> 5] >> (hr & 31)) |
+                            (coll[h >> 8] >> ((h >> 3) & 31))) & 1u;
+        const bool s = mark && t;
+        const uint32_t bal = __ballot_sync(kFull, s);
+        if (bal) {
+          uint32_t at = 0;
+          if (lane == 0) at = atomicAdd(&sh.n_susp, (uint32_t)__popc(bal));
+          at = __shfl_sync(kFull, at, 0);
+          const uint32_t i = at + __popc(bal & lt);
+          if (s && i < kHsSuspCap) susp[i] = d;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kHsThreads, 1) seed_search_hash_kernel(const SearchParams p) {
   extern __shared__ __align__(16) uint32_t dyn[];
   __shared__ HashShared sh;
@@ -1063,68 +1119,10 @@ __global__ void __launch_bounds__(kHsThreads, 1) seed_search_hash_kernel(const S
       __syncthreads();
 
       // ---- passes 1 and 2 over the same chunks
-      for (int pass = 1; pass <= 2; ++pass) {
-        for (uint32_t k0 = warp; k0 < C; k0 += kHsWarps * kHsUnroll) {
-          uint32_t pos[kHsUnroll], prev0[kHsUnroll], offs[kHsUnroll];
-          bool firstpos[kHsUnroll];
-#pragma unroll
-          for (int u = 0; u < kHsUnroll; ++u) {
-            const uint32_t k = k0 + u * kHsWarps;
-            pos[u] = kNone;
-            prev0[u] = kNone;
-            offs[u] = 0;
-            firstpos[u] = false;
-            if (k < C) {
-              const uint32_t j = sh.chunk_list[k];
-              const uint32_t b = sh.lbeg[j];
-              const uint32_t idx = b + 32u * (k - sh.pre[j]) + lane;
-              offs[u] = j * p.shift;
-              firstpos[u] = idx == b;
-              if (idx < sh.lend[j]) {
-                pos[u] = __ldg(p.positions + idx);
-                if (lane == 0 && idx > b) prev0[u] = __ldg(p.positions + idx - 1);
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < kHsUnroll; ++u) {
-            const uint32_t k = k0 + u * kHsWarps;
-            if (k >= C) break;                                   // warp-uniform
-            const bool valid = pos[u] != kNone;
-            const uint32_t d = (pos[u] - offs[u]) >> r;
-            uint32_t pv = __shfl_up_sync(kFull, pos[u], 1);
-            if (lane == 0) pv = prev0[u];
-            // first position of its list in region d: no predecessor, or predecessor elsewhere
-            const bool mark = valid && (firstpos[u] || pv == kNone || ((pv - offs[u]) >> r) != d);
-            const uint32_t h = d & hmask;
-            if (pass == 1) {
-              if (mark) {
-                const uint32_t bit = 1u << (h & 31);
-                const uint32_t old = atomicOr(&occ[h >> 5], bit);
-                if (old & bit) atomicOr(&coll[h >> 8], 1u << ((h >> 3) & 31));
-              }
-            } else {
-              bool s = false;
-              if (mark) {
-                const uint32_t hl = (h - 1) & hmask, hr = (h + 1) & hmask;
-                s = (((occ[hl >> 5] >> (hl & 31)) | (occ[hr >> 5] >> (hr & 31)) |
-                      (coll[h >> 8] >> ((h >> 3) & 31))) & 1u) != 0;
-              }
-              const uint32_t bal = __ballot_sync(kFull, s);
-              if (bal) {
-                uint32_t at = 0;
-                if (lane == 0) at = atomicAdd(&sh.n_susp, (uint32_t)__popc(bal));
-                at = __shfl_sync(kFull, at, 0);
-                if (s) {
-                  const uint32_t i = at + __popc(bal & lt);
-                  if (i < kHsSuspCap) susp[i] = d;
-                }
-              }
-            }
-          }
-        }
-        __syncthreads();
-      }
+      hs_stream<1>(p, sh, occ, coll, susp, C, warp, lane);
+      __syncthreads();
+      hs_stream<2>(p, sh, occ, coll, susp, C, warp, lane);
+      __syncthreads();
       bad = sh.n_susp > kHsSuspCap;
     }
 
