@@ -270,7 +270,7 @@ class Context:
         return hits, counts
 
     def set_search_variant(self, variant: int):
-        """3 = hash kernel (default), 2 = bucket kernel, 1 = sweep kernel, 0 = generic kernels."""
+        """2 = bucket kernel (default), 3 = hash kernel, 1 = sweep kernel, 0 = generic kernels."""
         self._check(self.L.gm_set_search_variant(self.h, int(variant)))
 
     def set_deferred_traceback(self, on: bool):

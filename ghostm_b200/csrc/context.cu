@@ -261,7 +261,7 @@ struct gm_context {
   bool chunk_tab_dirty = true;
   bool search_fast = true;   // balanced register-resident search kernel when the options allow it
   bool search_bucket = true; // bucket kernel (threshold 2) in front of it
-  bool search_hash = true;   // hash kernel (threshold 2) in front of both
+  bool search_hash = false;  // hash kernel (threshold 2) instead of the bucket kernel: variant 3 only
   bool traceback_fast = true;
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits

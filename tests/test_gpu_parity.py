@@ -34,7 +34,7 @@ def test_stage_parity(gpu_ctx, name, fast_search):
                 assert np.array_equal(ends, gends), np.flatnonzero(ends != gends)[:10]
                 n_stages += 1
     assert n_stages > 0
-    gpu_ctx.set_search_variant(3)
+    gpu_ctx.set_search_variant(2)
 
 
 @pytest.mark.parametrize("deferred,fast", [(True, 3), (True, 2), (False, 1), (False, 0)])
@@ -59,7 +59,7 @@ def test_hit_lists(gpu_ctx, name, deferred, fast):
             assert ok, (name, i, field, hits[i, :counts[i]], ref.hits[i, :counts[i]])
     assert int(ref.counts.sum()) > 0
     gpu_ctx.set_deferred_traceback(True)
-    gpu_ctx.set_search_variant(3)
+    gpu_ctx.set_search_variant(2)
 
 
 @pytest.mark.parametrize("name,world", [("small", 3), ("repeats", 2), ("options", 2), ("frames6", 4),
