@@ -729,73 +729,57 @@ __global__ void __launch_bounds__(NW * 32, MINB) seed_search_bucket_kernel(const
     }
     __syncthreads();
 
-    // ---- phase A: marks -> tile buckets.  Every warp takes a contiguous 1/NW share of every list
-    // (balanced although list lengths differ 100x) and walks it in batches of kBkUnroll x 32
-    // positions, ping-pong: the loads of the next batch (possibly of the next list) are in
-    // flight while the marks of the current one are scattered.  Inside a batch the predecessor
-    // of a position comes from the left lane; lane 0 takes it from lane 31 of the previous
-    // 32 positions, or - first positions of a batch - from one extra load.
+    // ---- phase A: marks -> tile buckets.  The warp walks its batches (up to kBkUnroll chunks of
+    // one list) with the loads of the next batch in flight while it scatters the current one.
     {
-      const uint32_t *__restrict__ positions = p.positions;
-      const uint32_t shift = p.shift, list_len = p.list_len;
-      struct Cur { uint32_t j, i0, hi, b; } cur = {0, 0, 0, 0};
-      // advance `cur` to the next non-empty batch; returns false at the end of the query
-      auto next_batch = [&](bool first) -> bool {
-        if (!first) {
-          cur.i0 += 32 * kBkUnroll;
-          if (cur.i0 < cur.hi) return true;
-          ++cur.j;
+      uint32_t j = 0, c = 0, lb = 0, le = 0, nj = 0;
+      auto seek = [&]() {   // first list >= j holding a chunk for this warp
+        while (j < p.list_len) {
+          lb = sh.lbeg[j];
+          le = sh.lend[j];
+          nj = (le - lb + 31) / 32;
+          c = (warp + NW - sh.pre[j] % NW) % NW;   // global chunk number (pre[j] + c) % NW == warp
+          if (c < nj) return;
+          ++j;
         }
-        for (; cur.j < list_len; ++cur.j) {
-          const uint32_t lb = sh.lbeg[cur.j], n = sh.lend[cur.j] - lb;
-          const uint32_t lo = lb + (uint32_t)(((unsigned long long)n * warp) / NW);
-          const uint32_t hi = lb + (uint32_t)(((unsigned long long)n * (warp + 1)) / NW);
-          if (lo < hi) { cur.b = lb; cur.i0 = lo; cur.hi = hi; return true; }
-        }
-        return false;
       };
-#define GM_BK_LOAD(POS, CARRY, OFF)                                                   \
-      {                                                                               \
-        _Pragma("unroll") for (int u = 0; u < kBkUnroll; ++u) {                       \
-          const uint32_t idx = cur.i0 + 32u * u + lane;                               \
-          POS[u] = idx < cur.hi ? __ldg(positions + idx) : kNone;                     \
-        }                                                                             \
-        CARRY = (lane == 0 && cur.i0 > cur.b) ? __ldg(positions + cur.i0 - 1) : kNone; \
-        OFF = cur.j * shift;                                                          \
+      auto load = [&](uint32_t (&pos)[kBkUnroll], uint32_t (&prev)[kBkUnroll]) {
+#pragma unroll
+        for (int u = 0; u < kBkUnroll; ++u) {
+          const uint32_t idx = lb + 32u * (c + u * NW) + lane;
+          pos[u] = kNone;
+          prev[u] = kNone;
+          if (j < p.list_len && idx < le) {
+            pos[u] = __ldg(p.positions + idx);
+            if (idx > lb) prev[u] = __ldg(p.positions + idx - 1);
+          }
+        }
+      };
+      seek();
+      uint32_t pos[kBkUnroll], prev[kBkUnroll];
+      load(pos, prev);
+      while (j < p.list_len) {
+        const uint32_t off = j * p.shift;
+        c += NW * kBkUnroll;
+        if (c >= nj) { ++j; seek(); }
+        uint32_t npos[kBkUnroll], nprev[kBkUnroll];
+        load(npos, nprev);
+#pragma unroll
+        for (int u = 0; u < kBkUnroll; ++u) {
+          if (pos[u] != kNone) {
+            const uint32_t d = (pos[u] - off) >> r;
+            if (prev[u] == kNone || ((prev[u] - off) >> r) != d) {   // first of its list in region d
+              const uint32_t t = d >> TB, x = d & xmask;
+              const uint32_t slot = atomicAdd(&sh.cnt[t], 1u);
+              if (slot < S) bucket[t * S + slot] = (uint16_t)x;
+              else sh.bad = 1;
+              if (x == 0) atomicOr(&sh.halo[t >> 5], 1u << (t & 31));
+            }
+          }
+          pos[u] = npos[u];
+          prev[u] = nprev[u];
+        }
       }
-#define GM_BK_SCATTER(POS, CARRY, OFF)                                                \
-      {                                                                               \
-        uint32_t carry = CARRY;                                                       \
-        _Pragma("unroll") for (int u = 0; u < kBkUnroll; ++u) {                       \
-          uint32_t pv = __shfl_up_sync(kFull, POS[u], 1);                             \
-          if (lane == 0) pv = carry;                                                  \
-          carry = __shfl_sync(kFull, POS[u], 31);                                     \
-          if (POS[u] != kNone) {                                                      \
-            const uint32_t d = (POS[u] - OFF) >> r;                                   \
-            if (pv == kNone || ((pv - OFF) >> r) != d) { /* first of its list in d */ \
-              const uint32_t t = d >> TB, x = d & xmask;                              \
-              const uint32_t slot = atomicAdd(&sh.cnt[t], 1u);                        \
-              if (slot < S) bucket[t * S + slot] = (uint16_t)x;                       \
-              else sh.bad = 1;                                                        \
-              if (x == 0) atomicOr(&sh.halo[t >> 5], 1u << (t & 31));                 \
-            }                                                                         \
-          }                                                                           \
-        }                                                                             \
-      }
-      uint32_t posA[kBkUnroll], posB[kBkUnroll], carryA = kNone, carryB = kNone, offA = 0, offB = 0;
-      bool more = next_batch(true);
-      if (more) GM_BK_LOAD(posA, carryA, offA)
-      while (more) {
-        more = next_batch(false);
-        if (more) GM_BK_LOAD(posB, carryB, offB)
-        GM_BK_SCATTER(posA, carryA, offA)
-        if (!more) break;
-        more = next_batch(false);
-        if (more) GM_BK_LOAD(posA, carryA, offA)
-        GM_BK_SCATTER(posB, carryB, offB)
-      }
-#undef GM_BK_LOAD
-#undef GM_BK_SCATTER
     }
     __syncthreads();
     bool bad = sh.bad != 0;
