@@ -59,3 +59,48 @@ def test_reference_host_linked_against_our_library(name, tmp_path):
     subprocess.check_call([DROPIN, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o", str(out),
                            "-D", "0", "-l", "1"] + meta["aln_args"])
     assert open(out, encoding="latin-1", newline="").read() == texts[0]
+
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ghostm")
+_CODON = ["GCT", "CGT", "AAT", "GAT", "TGT", "CAA", "GAA", "GGT", "CAT", "ATT", "CTT", "AAA", "ATG",
+          "TTT", "CCT", "TCT", "ACT", "TGG", "TAT", "GTT"]   # one codon per residue code A..V
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ghostm not built (needs /root/reference)")
+@pytest.mark.parametrize("n_reads,style", [(100_000, "0"), (20_000, "2")])
+def test_config2_standin_against_the_live_reference(n_reads, style, tmp_path):
+    """BASELINE config 2 stand-in (testset/large_queries.fasta is absent): 75-nt DNA
+    reads, half back-translated from db proteins with 10 % substitutions, half random, formatted
+    by the REFERENCE's own `db` and `qry -t d` (6-frame translation, six same-name queries per
+    read), aligned by the reference CPU aligner and by ghostm_b200_aln on the same files: the
+    output files must be byte-identical."""
+    import numpy as np
+    from ghostm_b200 import synth
+    rng = np.random.default_rng(20261018)
+    dbs, dbn = synth.protein_db(21, 1_000_000)
+    formats.write_fasta(str(tmp_path / "db.fa"), dbn, dbs, 70)
+    concat = np.concatenate(dbs)
+    from_db = rng.random(n_reads) < 0.5
+    starts = rng.integers(0, concat.shape[0] - 25, size=n_reads)
+    rand_nt = rng.integers(0, 4, size=(n_reads, 75))
+    sub = rng.random((n_reads, 75)) < 0.10
+    with open(tmp_path / "reads.fa", "w") as f:
+        for i in range(n_reads):
+            if from_db[i]:
+                nt = list("".join(_CODON[min(int(c), 19)] for c in concat[starts[i]:starts[i] + 25]))
+                for k in np.flatnonzero(sub[i]):
+                    nt[k] = "ACGT"[rand_nt[i, k]]
+                nt = "".join(nt)
+            else:
+                nt = "".join("ACGT"[x] for x in rand_nt[i])
+            f.write(f">r{i}\n{nt}\n")
+    quiet = dict(stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call([REF, "db", "-i", str(tmp_path / "db.fa"), "-o", str(tmp_path / "db")], **quiet)
+    subprocess.check_call([REF, "qry", "-t", "d", "-i", str(tmp_path / "reads.fa"), "-o", str(tmp_path / "q")], **quiet)
+    subprocess.check_call([REF, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o",
+                           str(tmp_path / "ref.txt"), "-y", style], **quiet)
+    subprocess.check_call([ALN, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o",
+                           str(tmp_path / "ours.txt"), "-D", "0", "-y", style], **quiet)
+    ref = (tmp_path / "ref.txt").read_bytes()
+    assert ref.count(b"\n") > n_reads // 4
+    assert (tmp_path / "ours.txt").read_bytes() == ref
