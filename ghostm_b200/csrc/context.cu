@@ -570,7 +570,6 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     p.query_counter = c->small.p + 0;
     p.positions_visited = c->counters.p + 1;
     p.overflow = reinterpret_cast<int *>(c->small.p + 2);
-    p.debug = getenv("GM_SEARCH_DEBUG") ? (uint32_t)atoi(getenv("GM_SEARCH_DEBUG")) : 0u;
     uint32_t tile_bits = 0, bucket_cap = 0, launches = 1;
     const bool hash = c->search_hash && c->search_fast &&
                       search_hash_ok(p.threshold, p.list_len, p.n_regions);

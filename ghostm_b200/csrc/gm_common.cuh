@@ -62,7 +62,6 @@ struct SearchParams {
   uint32_t *query_counter;     // dynamic query fetch
   unsigned long long *positions_visited;
   int *overflow;               // set when cand_capacity is exceeded
-  uint32_t debug;              // timing experiments only (GM_SEARCH_DEBUG), 0 in production
   const uint32_t *query_list;  // sweep kernels: process query_list[0..n_queries) instead of 0..n_queries
   // bucket kernel (threshold 2)
   uint32_t tile_bits;          // log2 regions per tile
