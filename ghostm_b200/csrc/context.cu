@@ -111,12 +111,12 @@ __global__ void gather_kernel(const uint32_t *cand_off, const uint32_t *cand_cnt
   }
 }
 
-// gm_candidates_pack: per-query candidate slices -> per-part [start | score | end] blocks in
+// gm_candidates_pack: per-query candidate slices -> per-part [score | end] blocks in
 // reference order.  prefix[] is the exclusive scan of cand_cnt over all queries.
 __global__ void pack_kernel(const uint32_t *cand_off, const uint32_t *cand_cnt,
                             const uint32_t *prefix, uint32_t n_q, const uint32_t *bounds,
-                            uint32_t n_parts, const uint32_t *start, const uint32_t *score,
-                            const uint32_t *end, uint32_t *out) {
+                            uint32_t n_parts, const uint32_t *score, const uint32_t *end,
+                            uint32_t *out) {
   for (uint32_t q = blockIdx.x; q < n_q; q += gridDim.x) {
     uint32_t lo = 0, hi = n_parts;  // bounds[lo] <= q < bounds[hi]
     while (hi - lo > 1) {
@@ -124,12 +124,11 @@ __global__ void pack_kernel(const uint32_t *cand_off, const uint32_t *cand_cnt,
       if (bounds[mid] <= q) lo = mid; else hi = mid;
     }
     const size_t part_base = prefix[bounds[lo]], m = prefix[bounds[lo + 1]] - part_base;
-    uint32_t *dst = out + 3 * part_base + (prefix[q] - part_base);
+    uint32_t *dst = out + 2 * part_base + (prefix[q] - part_base);
     const uint32_t off = cand_off[q], cnt = cand_cnt[q];
     for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-      dst[i] = start[off + i];
-      dst[m + i] = score[off + i];
-      dst[2 * m + i] = end[off + i];
+      dst[i] = score[off + i];
+      dst[m + i] = end[off + i];
     }
   }
 }
@@ -266,6 +265,7 @@ struct gm_context {
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits
   uint32_t serial = 0;
+  bool imported = false;           // resident candidates came from gm_candidates_import
   uint64_t search_fallbacks = 0;   // queries redone by the sweep kernel (bucket capacities exceeded)
 };
 
@@ -634,6 +634,7 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
   for (uint32_t v : c->h_counts) sum += v;
   c->cand_total = sum;
   c->cur_chunk = (int)id;
+  c->imported = false;
   if (counts) memcpy(counts, c->h_counts.data(), (size_t)c->n_queries * 4);
   if (total) *total = sum;
   return 0;
@@ -677,9 +678,11 @@ int scan_counts(gm_context *c, uint32_t first, uint32_t end, int mode, uint32_t 
   return 0;
 }
 
-int check_range(gm_context *c, uint32_t first, uint32_t end) {
+int check_range(gm_context *c, uint32_t first, uint32_t end, bool need_starts = false) {
   if (int r = ensure_query_state(c)) return r;
   if (c->cur_chunk < 0) return fail(GM_ERR_ARGUMENT, "no searched db chunk (gm_search)");
+  if (need_starts && c->imported)
+    return fail(GM_ERR_ARGUMENT, "imported candidates carry no region starts (gm_candidates_import)");
   if (first > end || end > c->n_queries) return fail(GM_ERR_ARGUMENT, "bad query range [%u,%u)", first, end);
   return 0;
 }
@@ -689,7 +692,7 @@ int check_range(gm_context *c, uint32_t first, uint32_t end) {
 extern "C" int gm_candidates_download(gm_context *c, uint32_t first, uint32_t end,
                                       uint32_t *query_ids, uint32_t *starts) {
   if (int r = check_ctx(c)) return r;
-  if (int r = check_range(c, first, end)) return r;
+  if (int r = check_range(c, first, end, true)) return r;
   if (first == end) return 0;
   uint32_t total = 0;
   if (int r = scan_counts(c, first, end, 0, &total)) return r;
@@ -727,9 +730,9 @@ extern "C" int gm_candidates_pack(gm_context *c, uint32_t n_parts, const uint32_
     GM_CUDA(cudaMemcpyAsync(counts_dev, c->cand_cnt.p, (size_t)c->n_queries * 4,
                             cudaMemcpyDeviceToDevice, c->stream));
   if (data_dev && total) {
-    if (3 * total > data_capacity_words)
+    if (2 * total > data_capacity_words)
       return fail(GM_ERR_CAPACITY, "pack buffer holds %llu words, %llu needed",
-                  (unsigned long long)data_capacity_words, (unsigned long long)(3 * total));
+                  (unsigned long long)data_capacity_words, (unsigned long long)(2 * total));
     if (!c->cand_score.p || !c->cand_end.p) return fail(GM_ERR_ARGUMENT, "candidates are not scored (gm_score)");
     if (int r = scan_counts(c, 0, c->n_queries, 0, nullptr)) return r;
     GM_CUDA(c->bounds.ensure(n_parts + 1));
@@ -737,8 +740,7 @@ extern "C" int gm_candidates_pack(gm_context *c, uint32_t n_parts, const uint32_
                             c->stream));
     pack_kernel<<<c->sm_count * 8, 128, 0, c->stream>>>(c->cand_off.p, c->cand_cnt.p, c->prefix.p,
                                                         c->n_queries, c->bounds.p, n_parts,
-                                                        c->cand_start.p, c->cand_score.p,
-                                                        c->cand_end.p, data_dev);
+                                                        c->cand_score.p, c->cand_end.p, data_dev);
     GM_CUDA(cudaGetLastError());
   }
   GM_CUDA(cudaStreamSynchronize(c->stream));
@@ -769,9 +771,8 @@ extern "C" int gm_candidates_import(gm_context *c, uint32_t id, const uint32_t *
   GM_CUDA(cudaMemcpyAsync(c->cand_off.p, c->prefix.p, (size_t)c->n_queries * 4,
                           cudaMemcpyDeviceToDevice, c->stream));
   if (total) {
-    GM_CUDA(cudaMemcpyAsync(c->cand_start.p, data_dev, total * 4, cudaMemcpyDeviceToDevice, c->stream));
-    GM_CUDA(cudaMemcpyAsync(c->cand_score.p, data_dev + total, total * 4, cudaMemcpyDeviceToDevice, c->stream));
-    GM_CUDA(cudaMemcpyAsync(c->cand_end.p, data_dev + 2 * total, total * 4, cudaMemcpyDeviceToDevice, c->stream));
+    GM_CUDA(cudaMemcpyAsync(c->cand_score.p, data_dev, total * 4, cudaMemcpyDeviceToDevice, c->stream));
+    GM_CUDA(cudaMemcpyAsync(c->cand_end.p, data_dev + total, total * 4, cudaMemcpyDeviceToDevice, c->stream));
   }
   GM_CUDA(cudaStreamSynchronize(c->stream));
   uint64_t sum = 0;
@@ -781,13 +782,14 @@ extern "C" int gm_candidates_import(gm_context *c, uint32_t id, const uint32_t *
                 (unsigned long long)total);
   c->cand_total = sum;
   c->cur_chunk = (int)id;
+  c->imported = true;   // no region starts behind the exchange: hits get db_start from TraceBack
   return 0;
 }
 
 extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *scores,
                         uint32_t *ends, gm_stats *stats) {
   if (int r = check_ctx(c)) return r;
-  if (int r = check_range(c, first, end)) return r;
+  if (int r = check_range(c, first, end, true)) return r;
   if (first == end) return 0;
   DbChunk &ch = c->chunks[c->cur_chunk];
   GM_CUDA(c->cand_score.ensure(c->cand_capacity));
@@ -972,7 +974,7 @@ extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *s
   p.end_query = end;
   p.cand_off = c->cand_off.p;
   p.cand_cnt = c->cand_cnt.p;
-  p.cand_start = c->cand_start.p;
+  p.cand_start = c->imported ? nullptr : c->cand_start.p;
   p.cand_score = c->cand_score.p;
   p.cand_end = c->cand_end.p;
   p.db = ch.seq.p;

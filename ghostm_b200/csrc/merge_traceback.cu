@@ -343,7 +343,7 @@ __device__ void merge_run(const MergeParams &p, Rec *list, Pos *scratch, uint32_
           h.db_id = db_id;
           h.db_chunk = p.db_chunk;
           h.score = p.cand_score[g];
-          h.db_start = p.cand_start[g];
+          h.db_start = p.cand_start ? p.cand_start[g] : 0u;   // placeholder until TraceBack (:941)
           h.db_end = end;          // absolute; TraceBack makes both sequence-relative
           h.aln_len = p.serial;    // accepted by this call ...
           h.aln_match = kNoId;     // ... TraceBack pending

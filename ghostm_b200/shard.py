@@ -12,8 +12,8 @@ per same-name run, aligner.cpp:697-742).  That gives two independent axes:
          scored candidates of ALL chunks in ascending chunk order, the .pos tables (DB::GetID)
          and the residues (TraceBack windows) - 1 B per residue, replicated on every rank.
 
-Between them every rank hands every other rank the candidates (start, score, end) of that
-rank's query slice: one all-to-all per round of N chunks, ~12 B per candidate over NVLink.  The
+Between them every rank hands every other rank the candidates (score, end) of that
+rank's query slice: one all-to-all per round of N chunks, 8 B per candidate over NVLink.  The
 slices are cut at same-name run boundaries; every slice then sees, for every chunk, exactly
 the Merge calls (candidate-chunk segments, aligner.cpp:131-171) the single-device run makes,
 restricted to its own queries - including the calls that bring it no candidate, because Merge
@@ -30,6 +30,9 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 MAX_SEGMENTS = 15     # candidate chunks per (query chunk, db chunk) the meta exchange carries
+BLOCK_WORDS = 2       # words per exchanged candidate: SW score and forward end.  The candidate's
+                      # region start is not needed behind the exchange: Merge only copies it into
+                      # the hit and TraceBack overwrites it (aligner.cpp:941)
 
 Segment = Tuple[int, int]
 
@@ -69,8 +72,8 @@ class Front:
         raise NotImplementedError
 
     def pack(self, bounds: np.ndarray):
-        """-> (counts int32 tensor [n_queries], data int32 tensor [3 * total], totals uint64
-        ndarray [len(bounds) - 1]); data holds one [start | score | end] block per slice."""
+        """-> (counts int32 tensor [n_queries], data int32 tensor [2 * total], totals uint64
+        ndarray [len(bounds) - 1]); data holds one [score | end] block per slice."""
         raise NotImplementedError
 
     def empty(self, bounds: np.ndarray):
@@ -112,7 +115,7 @@ def _meta_unpack(m: np.ndarray):
 def exchange(dist, rank: int, world: int, bounds: np.ndarray, counts, data, totals: np.ndarray,
              segs: Sequence[Segment]):
     """All-to-all of one round: returns, per source rank s, (counts of my slice, the
-    [start | score | end] block of my slice, its candidate count, the segments of s's chunk)."""
+    [score | end] block of my slice, its candidate count, the segments of s's chunk)."""
     import torch
     dev = counts.device
     meta = torch.from_numpy(_meta_pack(segs, totals, world)).to(dev)
@@ -124,13 +127,13 @@ def exchange(dist, rank: int, world: int, bounds: np.ndarray, counts, data, tota
     counts_in = torch.empty(world * n_slice, dtype=counts.dtype, device=dev)
     dist.all_to_all_single(counts_in, counts, [n_slice] * world,
                            [int(bounds[p + 1]) - int(bounds[p]) for p in range(world)])
-    data_in = torch.empty(3 * sum(recv_tot), dtype=data.dtype, device=dev)
-    dist.all_to_all_single(data_in, data, [3 * m for m in recv_tot], [3 * int(t) for t in totals])
+    data_in = torch.empty(BLOCK_WORDS * sum(recv_tot), dtype=data.dtype, device=dev)
+    dist.all_to_all_single(data_in, data, [BLOCK_WORDS * m for m in recv_tot], [BLOCK_WORDS * int(t) for t in totals])
     inbox, off = [], 0
     for s in range(world):
-        inbox.append((counts_in[s * n_slice:(s + 1) * n_slice], data_in[off:off + 3 * recv_tot[s]],
+        inbox.append((counts_in[s * n_slice:(s + 1) * n_slice], data_in[off:off + BLOCK_WORDS * recv_tot[s]],
                       recv_tot[s], _meta_unpack(meta_all[s])[0]))
-        off += 3 * recv_tot[s]
+        off += BLOCK_WORDS * recv_tot[s]
     return inbox
 
 
@@ -143,10 +146,10 @@ def exchange_local(outboxes, bounds: np.ndarray):
         inbox = []
         for s in range(world):
             counts, data, totals, segs = outboxes[s]
-            off = 3 * int(sum(int(t) for t in totals[:r]))
+            off = BLOCK_WORDS * int(sum(int(t) for t in totals[:r]))
             m = int(totals[r])
             inbox.append((counts[int(bounds[r]):int(bounds[r + 1])].clone(),
-                          data[off:off + 3 * m].clone(), m, list(segs)))
+                          data[off:off + BLOCK_WORDS * m].clone(), m, list(segs)))
         inboxes.append(inbox)
     return inboxes
 
@@ -223,7 +226,7 @@ class GpuFront(Front):
         self.ctx, self.stats, self.n = ctx, stats, n_queries
         self.launches = 0                # kernels launched by pack (scan + pack)
         self.counts = torch.zeros(n_queries, dtype=torch.int32, device=device)
-        self.data = torch.empty(3 * capacity, dtype=torch.int32, device=device)
+        self.data = torch.empty(BLOCK_WORDS * capacity, dtype=torch.int32, device=device)
 
     def prepare(self, chunk_id: int) -> List[Segment]:
         from . import capi
@@ -244,7 +247,7 @@ class GpuFront(Front):
         totals = self.ctx.candidates_pack(bounds, self.counts.data_ptr(), self.data.data_ptr(),
                                           self.data.numel())
         self.launches += 2
-        return self.counts, self.data[:3 * int(totals.sum())], totals
+        return self.counts, self.data[:BLOCK_WORDS * int(totals.sum())], totals
 
     def empty(self, bounds: np.ndarray):
         self.counts.zero_()

@@ -239,16 +239,17 @@ int gm_db_upload_seq(gm_context *ctx, uint32_t chunk_id, const uint8_t *seq, uin
 /* Pack the scored candidates of the searched chunk by query slice.  bounds[n_parts + 1] are
  * ascending query indices (bounds[0] = 0, bounds[n_parts] = n_queries).  DEVICE outputs:
  * counts_dev[n_queries] = per-query candidate counts; data_dev = for every part p a block
- * [start[m_p] | score[m_p] | end[m_p]] in reference order (query, then region, ascending),
- * blocks in part order, 3 * sum(m_p) words in total (data_capacity_words is checked).
+ * [score[m_p] | end[m_p]] in reference order (query, then region, ascending), blocks in part
+ * order, 2 * sum(m_p) words in total (data_capacity_words is checked).  The region starts stay
+ * behind: Merge only copies them into the hits and TraceBack overwrites them (aligner.cpp:941).
  * HOST output: part_totals[n_parts] = m_p.  data_dev may be NULL (totals only). */
 int gm_candidates_pack(gm_context *ctx, uint32_t n_parts, const uint32_t *bounds,
                        uint32_t *counts_dev, uint32_t *data_dev, uint64_t data_capacity_words,
                        uint64_t *part_totals);
 /* Install scored candidates of db chunk chunk_id (resident, possibly sequence-only) for ALL
  * resident queries from DEVICE buffers laid out like one gm_candidates_pack part: counts_dev
- * [n_queries] and data_dev = [start[total] | score[total] | end[total]].  Afterwards gm_merge
- * behaves as after gm_search + gm_score on that chunk. */
+ * [n_queries] and data_dev = [score[total] | end[total]].  Afterwards gm_merge behaves as after
+ * gm_search + gm_score on that chunk (hits carry db_start = 0 until TraceBack has run). */
 int gm_candidates_import(gm_context *ctx, uint32_t chunk_id, const uint32_t *counts_dev,
                          const uint32_t *data_dev, uint64_t total);
 
