@@ -26,7 +26,7 @@ EXTENDED_SYMBOLS = ["gm_version", "gm_last_error", "gm_device_count", "gm_create
                     "gm_results_device", "gm_stream", "gm_measure_dpx_peak",
                     "gm_set_deferred_traceback", "gm_traceback_pending", "gm_set_search_variant",
                     "gm_align_prepare", "gm_align_merge", "gm_db_upload_seq", "gm_candidates_pack",
-                    "gm_candidates_import"]
+                    "gm_candidates_import", "gm_candidates_transfer"]
 
 HIT_DTYPE = np.dtype([("query_id", "<u4"), ("db_id", "<u4"), ("db_chunk", "<u4"), ("score", "<u4"),
                       ("db_start", "<u4"), ("db_end", "<u4"), ("aln_len", "<u4"),
@@ -81,6 +81,7 @@ def load():
     L.gm_db_upload_seq.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
     L.gm_candidates_pack.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_uint64, vp]
     L.gm_candidates_import.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint64]
+    L.gm_candidates_transfer.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]
     L.gm_db_release.argtypes = [vp, C.c_uint32]
     L.gm_query_upload.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
     L.gm_align_chunk.argtypes = [vp, C.c_uint32, C.POINTER(GmStats)]
@@ -206,6 +207,10 @@ class Context:
 
     def candidates_import(self, chunk_id: int, counts_ptr: int, data_ptr: int, total: int):
         self._check(self.L.gm_candidates_import(self.h, chunk_id, counts_ptr, data_ptr or None, total))
+
+    def candidates_transfer_to(self, dst: "Context", chunk_id: int, first: int, end: int):
+        """gm_candidates_transfer: my scored candidates of queries [first, end) -> dst."""
+        self._check(self.L.gm_candidates_transfer(self.h, dst.h, chunk_id, first, end))
 
     def db_build_index(self, chunk_id: int, seq: np.ndarray, seq_starts: np.ndarray, seed: int):
         seq = np.ascontiguousarray(seq, dtype=np.uint8)

@@ -786,6 +786,63 @@ extern "C" int gm_candidates_import(gm_context *c, uint32_t id, const uint32_t *
   return 0;
 }
 
+extern "C" int gm_candidates_transfer(gm_context *src, gm_context *dst, uint32_t id, uint32_t first,
+                                      uint32_t end) {
+  if (!src || !dst || src == dst) return fail(GM_ERR_ARGUMENT, "two distinct contexts are required");
+  if (int r = check_ctx(dst)) return r;
+  if (int r = ensure_query_state(dst)) return r;
+  if (id >= GM_MAX_DB_CHUNKS || !dst->chunks[id].valid)
+    return fail(GM_ERR_ARGUMENT, "db chunk %u is not resident in the receiving context", id);
+  if (int r = check_ctx(src)) return r;
+  if (int r = check_range(src, first, end, true)) return r;
+  if (src->cur_chunk != (int)id) return fail(GM_ERR_ARGUMENT, "the sending context holds chunk %d, not %u", src->cur_chunk, id);
+  if (end - first != dst->n_queries)
+    return fail(GM_ERR_ARGUMENT, "slice [%u,%u) does not match the %u queries of the receiving context",
+                first, end, dst->n_queries);
+  if (!src->cand_score.p || !src->cand_end.p) return fail(GM_ERR_ARGUMENT, "candidates are not scored (gm_score)");
+  uint64_t total = 0;
+  for (uint32_t q = first; q < end; ++q) total += src->h_counts[q];
+  if (total > dst->cand_capacity)
+    return fail(GM_ERR_CAPACITY, "candidate buffer (%llu entries) too small for %llu transferred; raise "
+                "it with gm_set_candidate_capacity", (unsigned long long)dst->cand_capacity,
+                (unsigned long long)total);
+  // sending side: the slice in reference order (query, region ascending), on its own stream
+  if (total) {
+    if (int r = scan_counts(src, first, end, 0, nullptr)) return r;
+    GM_CUDA(src->gather0.ensure(total));
+    GM_CUDA(src->gather1.ensure(total));
+    gather_kernel<<<src->sm_count * 4, 128, 0, src->stream>>>(
+        src->cand_off.p, src->cand_cnt.p, src->prefix.p, first, end - first, src->cand_score.p,
+        src->cand_end.p, src->gather0.p, src->gather1.p, nullptr);
+    GM_CUDA(cudaGetLastError());
+  }
+  // receiving side buffers (allocated under the receiver's device)
+  if (int r = check_ctx(dst)) return r;
+  dst->cur_chunk = -1;
+  GM_CUDA(dst->cand_start.ensure(dst->cand_capacity));
+  GM_CUDA(dst->cand_score.ensure(dst->cand_capacity));
+  GM_CUDA(dst->cand_end.ensure(dst->cand_capacity));
+  if (int r = check_ctx(src)) return r;
+  // device to device over NVLink (peer copy; staged by the driver when there is no peer access)
+  GM_CUDA(cudaMemcpyPeerAsync(dst->cand_cnt.p, dst->device, src->cand_cnt.p + first, src->device,
+                              (size_t)(end - first) * 4, src->stream));
+  if (total) {
+    GM_CUDA(cudaMemcpyPeerAsync(dst->cand_score.p, dst->device, src->gather0.p, src->device, total * 4, src->stream));
+    GM_CUDA(cudaMemcpyPeerAsync(dst->cand_end.p, dst->device, src->gather1.p, src->device, total * 4, src->stream));
+  }
+  GM_CUDA(cudaStreamSynchronize(src->stream));
+  if (int r = check_ctx(dst)) return r;
+  dst->h_counts.assign(src->h_counts.begin() + first, src->h_counts.begin() + end);
+  if (int r = scan_counts(dst, 0, dst->n_queries, 0, nullptr)) return r;
+  GM_CUDA(cudaMemcpyAsync(dst->cand_off.p, dst->prefix.p, (size_t)dst->n_queries * 4,
+                          cudaMemcpyDeviceToDevice, dst->stream));
+  GM_CUDA(cudaStreamSynchronize(dst->stream));
+  dst->cand_total = total;
+  dst->cur_chunk = (int)id;
+  dst->imported = true;
+  return 0;
+}
+
 extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *scores,
                         uint32_t *ends, gm_stats *stats) {
   if (int r = check_ctx(c)) return r;

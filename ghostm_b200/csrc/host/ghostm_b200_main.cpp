@@ -5,9 +5,11 @@
 // search itself - seed lookup, candidate chunking, SW extension, Merge, TraceBack - runs on the
 // GPU through the C ABI of include/ghostm_b200.h; nothing here computes an alignment and there is
 // no CPU fallback.  `-D` takes one device id like the reference, or a comma separated list: the
-// db chunks are then spread round-robin over the devices and the per-query hit lists are handed
-// from device to device in db order through host memory, which keeps the result identical to a
-// single-device (and to the reference's) run.
+// db chunks (index) are then spread round-robin over the devices for seed search + SW extension,
+// the scored candidates go device to device by query slice (gm_candidates_transfer) and every
+// device runs Merge + TraceBack for its slice of the queries over all chunks in ascending order
+// (DESIGN.md section 8), which keeps the result identical to a single-device (and to the
+// reference's) run.
 #include <getopt.h>
 #include <math.h>
 #include <stdint.h>
@@ -262,34 +264,58 @@ void check(int rc, const char *what) {
   if (rc != 0) throw std::runtime_error(std::string(what) + ": " + gm_last_error());
 }
 
-// ---- hit list exchange between devices, in db-chunk order -------------------------------------
-struct Baton {           // which db chunk may merge next, and the lists it starts from
-  std::mutex mu;
-  std::condition_variable cv;
-  uint32_t next_chunk = 0;
-  std::vector<gm_hit> hits;
-  std::vector<uint32_t> counts;
+// ---- several devices: chunk-parallel front, query-sliced back ------------
+struct Segment { uint32_t first, end; };   // one candidate chunk = one Merge call (aligner.cpp:131-171)
+
+// Slice boundaries at same-name run starts, about n / world queries each.
+std::vector<uint32_t> slice_bounds(const std::vector<uint8_t> &name_break, uint32_t n, size_t world) {
+  std::vector<uint32_t> bounds(world + 1, 0);
+  for (size_t r = 1; r < world; ++r) {
+    uint32_t b = (uint32_t)(((uint64_t)r * n + world / 2) / world);
+    while (b < n && b > 0 && !name_break[b]) ++b;   // next run start at or after the target
+    bounds[r] = std::max(b, bounds[r - 1]);
+  }
+  bounds[world] = n;
+  return bounds;
+}
+
+// Seed search + SW extension of one db chunk for all queries; the candidate-chunk segments.
+std::vector<Segment> front_chunk(gm_context *ctx, uint32_t chunk, uint32_t n_queries, uint32_t max_list_length) {
+  std::vector<uint32_t> counts(n_queries);
+  uint64_t total = 0;
+  check(gm_search(ctx, chunk, counts.data(), &total, nullptr), "gm_search");
+  std::vector<Segment> segs;
+  uint32_t first = 0;
+  while (true) {
+    uint64_t n = 0;
+    int last = 0;
+    const uint32_t end = gm_chunk_rule(counts.data(), n_queries, first, max_list_length, &n, &last);
+    if (n == 0) break;                                   // aligner.cpp:136-139
+    check(gm_score(ctx, first, end, nullptr, nullptr, nullptr), "gm_score");
+    segs.push_back(Segment{first, end});
+    if (last) break;
+    first = end;
+  }
+  return segs;
+}
+
+struct Shard {            // one device of a multi-device run
+  gm_context *front = nullptr, *back = nullptr;
+  std::mutex front_mu;    // gm_candidates_transfer is serialised per sending context
+  std::vector<Segment> segs;
   std::string error;
 };
 
-void device_worker(gm_context *ctx, const std::vector<int> &my_chunks, bool single_device, Baton *baton) {
-  try {
-    for (int c : my_chunks) {
-      check(gm_align_prepare(ctx, (uint32_t)c, nullptr), "gm_align_prepare");
-      std::unique_lock<std::mutex> lock(baton->mu);
-      baton->cv.wait(lock, [&] { return baton->next_chunk == (uint32_t)c || !baton->error.empty(); });
-      if (!baton->error.empty()) return;
-      if (!single_device && c > 0) check(gm_results_upload(ctx, baton->hits.data(), baton->counts.data()), "gm_results_upload");
-      check(gm_align_merge(ctx, nullptr), "gm_align_merge");
-      if (!single_device) check(gm_results_download(ctx, baton->hits.data(), baton->counts.data()), "gm_results_download");
-      baton->next_chunk = (uint32_t)c + 1;
-      baton->cv.notify_all();
-    }
-  } catch (std::exception &e) {
-    std::lock_guard<std::mutex> lock(baton->mu);
-    baton->error = e.what();
-    baton->cv.notify_all();
-  }
+template <typename F>
+void on_every_device(std::vector<Shard> &shards, F body) {
+  std::vector<std::thread> workers;
+  for (size_t d = 0; d < shards.size(); ++d)
+    workers.emplace_back([&shards, &body, d] {
+      try { body(d); } catch (std::exception &e) { shards[d].error = e.what(); }
+    });
+  for (auto &w : workers) w.join();
+  for (auto &sh : shards)
+    if (!sh.error.empty()) throw std::runtime_error(sh.error);
 }
 
 // ---- output (aligner.cpp:951-1012) -------------------------------------------------------------
@@ -339,7 +365,6 @@ int run_aln(int argc, char **argv) {
     return 0;
   }
   const size_t n_dev = o.devices.size();
-  std::vector<gm_context *> ctx(n_dev, nullptr);
   gm_options go;
   memset(&go, 0, sizeof(go));
   go.seed = info.seed;
@@ -352,14 +377,21 @@ int run_aln(int argc, char **argv) {
   go.open_gap = o.open_gap;
   go.extend_gap = o.extend_gap;
   memcpy(go.score_matrix, sm.m, sizeof(go.score_matrix));
+  // one device: a single context does everything.  Several devices: per device a front context
+  // (index of the owned chunks, all queries) and a back context (residues + .pos of every chunk,
+  // the device's slice of the queries).
+  std::vector<Shard> shards(n_dev);
   for (size_t d = 0; d < n_dev; ++d) {
-    check(gm_create(o.devices[d], &ctx[d]), "gm_create");
-    check(gm_set_options(ctx[d], &go), "gm_set_options");
-    check(gm_set_deferred_traceback(ctx[d], n_dev == 1), "gm_set_deferred_traceback");
+    check(gm_create(o.devices[d], &shards[d].front), "gm_create");
+    check(gm_set_options(shards[d].front, &go), "gm_set_options");
+    if (n_dev > 1) {
+      check(gm_create(o.devices[d], &shards[d].back), "gm_create");
+      check(gm_set_options(shards[d].back, &go), "gm_set_options");
+    }
   }
   // db chunks: resident for the whole run (the reference re-reads them per query chunk)
   std::vector<DbChunk> names(info.division);
-  std::vector<std::vector<int>> owned(n_dev);
+  const uint32_t n_chunks = (uint32_t)info.division;
   for (int c = 0; c < info.division; ++c) {
     DbChunk full;
     if (!read_db_chunk(o.db, c, &full, true)) {
@@ -367,10 +399,13 @@ int run_aln(int argc, char **argv) {
       return 0;
     }
     const size_t d = (size_t)c % n_dev;
-    check(gm_db_upload(ctx[d], (uint32_t)c, full.seq.data(), full.seq_len, full.keys_count.data(),
+    check(gm_db_upload(shards[d].front, (uint32_t)c, full.seq.data(), full.seq_len, full.keys_count.data(),
                        (uint32_t)full.keys_count.size(), full.positions.data(), (uint32_t)full.positions.size(),
                        full.seq_starts.data(), full.n_seqs), "gm_db_upload");
-    owned[d].push_back(c);
+    if (n_dev > 1)
+      for (auto &sh : shards)
+        check(gm_db_upload_seq(sh.back, (uint32_t)c, full.seq.data(), full.seq_len, full.seq_starts.data(),
+                               full.n_seqs), "gm_db_upload_seq");
     names[c].names.swap(full.names);
     if (o.verbose) std::cout << "  db chunk " << c << " -> device " << o.devices[d] << std::endl;
   }
@@ -387,30 +422,72 @@ int run_aln(int argc, char **argv) {
     while (true) {
       std::vector<uint8_t> name_break(q.n, 0);
       for (uint32_t i = 1; i < q.n; ++i) name_break[i] = q.names[i] != q.names[i - 1];
-      uint64_t budget = std::min<uint64_t>((uint64_t)q.n * 2048 + (1u << 22), (1ull << 32) - 1);
-      for (size_t d = 0; d < n_dev; ++d) {
-        check(gm_set_candidate_capacity(ctx[d], budget), "gm_set_candidate_capacity");
-        check(gm_query_upload(ctx[d], q.seqs.data(), q.n, q.length, name_break.data()), "gm_query_upload");
-      }
-      Baton baton;
-      baton.hits.assign((size_t)q.n * cap, gm_hit());
-      baton.counts.assign(q.n, 0);
-      std::vector<std::thread> workers;
-      for (size_t d = 0; d < n_dev; ++d)
-        workers.emplace_back(device_worker, ctx[d], std::cref(owned[d]), n_dev == 1, &baton);
-      for (auto &w : workers) w.join();
-      if (!baton.error.empty()) throw std::runtime_error(baton.error);
+      const uint64_t budget = std::min<uint64_t>((uint64_t)q.n * 2048 + (1u << 22), (1ull << 32) - 1);
+      std::vector<gm_hit> hits((size_t)q.n * cap, gm_hit());
+      std::vector<uint32_t> counts(q.n, 0);
       if (n_dev == 1) {
-        check(gm_results_download(ctx[0], baton.hits.data(), baton.counts.data()), "gm_results_download");
+        gm_context *ctx = shards[0].front;
+        check(gm_set_candidate_capacity(ctx, budget), "gm_set_candidate_capacity");
+        check(gm_query_upload(ctx, q.seqs.data(), q.n, q.length, name_break.data()), "gm_query_upload");
+        for (uint32_t c = 0; c < n_chunks; ++c) check(gm_align_chunk(ctx, c, nullptr), "gm_align_chunk");
+        check(gm_results_download(ctx, hits.data(), counts.data()), "gm_results_download");
       } else {
-        // TraceBack ran inside every Merge on the owning device: the last lists are complete
+        const std::vector<uint32_t> bounds = slice_bounds(name_break, q.n, n_dev);
+        on_every_device(shards, [&](size_t d) {
+          Shard &sh = shards[d];
+          const uint32_t base = bounds[d], stop = bounds[d + 1];
+          check(gm_set_candidate_capacity(sh.front, budget), "gm_set_candidate_capacity");
+          check(gm_query_upload(sh.front, q.seqs.data(), q.n, q.length, name_break.data()), "gm_query_upload");
+          if (stop > base) {
+            check(gm_set_candidate_capacity(sh.back, budget), "gm_set_candidate_capacity");
+            check(gm_query_upload(sh.back, q.seqs.data() + (size_t)base * q.length, stop - base, q.length,
+                                  name_break.data() + base), "gm_query_upload");
+          }
+        });
+        for (uint32_t round0 = 0; round0 < n_chunks; round0 += (uint32_t)n_dev) {
+          on_every_device(shards, [&](size_t d) {          // front: the owned chunk of this round
+            const uint32_t c = round0 + (uint32_t)d;
+            shards[d].segs.clear();
+            if (c < n_chunks) shards[d].segs = front_chunk(shards[d].front, c, q.n, o.max_list_length);
+          });
+          on_every_device(shards, [&](size_t r) {          // back: the round's chunks, ascending
+            const uint32_t base = bounds[r], stop = bounds[r + 1];
+            if (stop == base) return;
+            for (size_t s = 0; s < n_dev; ++s) {
+              const uint32_t c = round0 + (uint32_t)s;
+              if (c >= n_chunks) break;
+              if (shards[s].segs.empty()) continue;        // empty list: no Merge call (aligner.cpp:136)
+              {
+                std::lock_guard<std::mutex> lock(shards[s].front_mu);
+                check(gm_candidates_transfer(shards[s].front, shards[r].back, c, base, stop),
+                      "gm_candidates_transfer");
+              }
+              for (const Segment &g : shards[s].segs) {    // one Merge call per candidate chunk
+                uint32_t f = std::min(std::max(g.first, base), stop), e = std::max(std::min(g.end, stop), base);
+                if (f >= e) f = e = base;                  // carried lists only (aligner.cpp:702)
+                check(gm_merge(shards[r].back, f - base, e - base, nullptr), "gm_merge");
+              }
+            }
+          });
+        }
+        on_every_device(shards, [&](size_t r) {            // TraceBack of the survivors, lists home
+          const uint32_t base = bounds[r], stop = bounds[r + 1];
+          if (stop == base) return;
+          check(gm_results_download(shards[r].back, hits.data() + (size_t)base * cap, counts.data() + base),
+                "gm_results_download");
+          for (uint32_t i = base; i < stop; ++i)
+            for (uint32_t k = 0; k < counts[i]; ++k) hits[(size_t)i * cap + k].query_id += base;
+        });
       }
-      write_hits(out, o, q, baton.hits, baton.counts, cap, names, (uint32_t)info.sum_length, karlin);
+      write_hits(out, o, q, hits, counts, cap, names, (uint32_t)info.sum_length, karlin);
       ++qi;  // aligner.cpp:201-203
       if (qi > o.end_chunk || qi >= (uint32_t)q_division || !read_query_chunk(o.queries, qi, &q)) break;
     }
   }
-  for (auto *c : ctx) gm_destroy(c);
+  for (auto &sh : shards) {
+    gm_destroy(sh.front);
+    if (sh.back) gm_destroy(sh.back);
+  }
   out.close();
   if (o.verbose) std::cout << "Complete." << std::endl;
   return 0;

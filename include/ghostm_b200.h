@@ -253,6 +253,13 @@ int gm_candidates_pack(gm_context *ctx, uint32_t n_parts, const uint32_t *bounds
 int gm_candidates_import(gm_context *ctx, uint32_t chunk_id, const uint32_t *counts_dev,
                          const uint32_t *data_dev, uint64_t total);
 
+/* Single process, several devices: pack + exchange + import in one call.  The scored candidates
+ * of src's searched chunk chunk_id for queries [first_query, end_query) go to dst, whose resident
+ * queries must be exactly that slice; device to device (cudaMemcpyPeerAsync: NVLink when peer
+ * access exists).  Not thread safe per context: serialise calls that share a src or a dst. */
+int gm_candidates_transfer(gm_context *src, gm_context *dst, uint32_t chunk_id,
+                           uint32_t first_query, uint32_t end_query);
+
 /* Device-side synthetic data and index construction (bench only; db_creator.cpp:167-241). */
 int gm_db_build_index(gm_context *ctx, uint32_t chunk_id, const uint8_t *seq, uint32_t seq_len,
                       const uint32_t *seq_starts, uint32_t n_seqs, uint32_t seed);

@@ -1,7 +1,8 @@
 """-m gpu: the drop-in boundary end to end.
   * ghostm_b200_aln (C++ host driver over the extended C ABI) must write the same output files as
-    the reference's `ghostm aln`, for all three output styles, on one device and - when two are
-    visible - with the db chunks spread over two devices;
+    the reference's `ghostm aln`, for all three output styles, on one device, with the db chunks
+    and query slices spread over several shards of one device and - when two are visible - over
+    two devices;
   * oracle/_ref/ghostm_dropin = the UNMODIFIED reference host objects linked against
     libghostm_b200.so: `aln -D 0` drives the ten legacy symbols exactly as the reference does."""
 import os
@@ -41,7 +42,9 @@ def _gpu_count():
 def test_host_driver_output_files(name, tmp_path):
     assert os.path.exists(ALN), "build with make -C ghostm_b200/csrc"
     meta, texts = _materialise(name, tmp_path)
-    devices = ["0"] + (["0,1"] if _gpu_count() >= 2 else [])
+    # "0,0": two shards on one device - the multi-device code path (front/back split, candidate
+    # transfer by query slice) runs even when a single GPU is visible
+    devices = ["0", "0,0", "0,0,0"] + (["0,1"] if _gpu_count() >= 2 else [])
     for dev in devices:
         for y, expect in texts.items():
             out = tmp_path / f"out_{y}_{dev.replace(',', '_')}.txt"
@@ -99,8 +102,9 @@ def test_config2_standin_against_the_live_reference(n_reads, style, tmp_path):
     subprocess.check_call([REF, "qry", "-t", "d", "-i", str(tmp_path / "reads.fa"), "-o", str(tmp_path / "q")], **quiet)
     subprocess.check_call([REF, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o",
                            str(tmp_path / "ref.txt"), "-y", style], **quiet)
-    subprocess.check_call([ALN, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o",
-                           str(tmp_path / "ours.txt"), "-D", "0", "-y", style], **quiet)
     ref = (tmp_path / "ref.txt").read_bytes()
     assert ref.count(b"\n") > n_reads // 4
-    assert (tmp_path / "ours.txt").read_bytes() == ref
+    for dev in (["0", "0,0"] if n_reads <= 20_000 else ["0"]):
+        subprocess.check_call([ALN, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o",
+                               str(tmp_path / "ours.txt"), "-D", dev, "-y", style], **quiet)
+        assert (tmp_path / "ours.txt").read_bytes() == ref, dev
