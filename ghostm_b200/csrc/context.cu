@@ -111,12 +111,6 @@ __global__ void gather_kernel(const uint32_t *cand_off, const uint32_t *cand_cnt
   }
 }
 
-// half task -> query table of the SW kernel: prefix[] is the exclusive scan of ceil(cnt/32)
-__global__ void half_table_kernel(const uint32_t *prefix, uint32_t n_q, uint32_t *half_query) {
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_q; q += gridDim.x * blockDim.x)
-    for (uint32_t h = prefix[q]; h < prefix[q + 1]; ++h) half_query[h] = q;
-}
-
 // gm_candidates_pack: per-query candidate slices -> per-part [score | end] blocks in
 // reference order.  prefix[] is the exclusive scan of cand_cnt over all queries.
 __global__ void pack_kernel(const uint32_t *cand_off, const uint32_t *cand_cnt,
@@ -248,7 +242,6 @@ struct gm_context {
   DevBuf<uint32_t> bounds;            // gm_candidates_pack part boundaries
   DevBuf<uint32_t> gather0, gather1, gather2;
   DevBuf<uint32_t> strip_scratch;
-  DevBuf<uint32_t> half_query;        // SW half task -> query
   DevBuf<unsigned long long> counters;  // [0] cand cursor [1] positions visited [2] cells [3] big cursor
   DevBuf<uint32_t> small;               // [0] query counter [1] task counter [2] overflow [3] n_jobs
                                         // [4] merge error [5] run counter [6] search fallbacks
@@ -369,7 +362,7 @@ extern "C" void gm_destroy(gm_context *c) {
   c->matrix.release(); c->queries.release(); c->run_first.release(); c->run_last.release();
   c->cand_off.release(); c->cand_cnt.release(); c->cand_start.release(); c->cand_score.release();
   c->cand_end.release(); c->staging.release(); c->prefix.release(); c->gather0.release();
-  c->gather1.release(); c->gather2.release(); c->bounds.release(); c->buckets.release(); c->fallback.release(); c->half_query.release(); c->strip_scratch.release(); c->counters.release();
+  c->gather1.release(); c->gather2.release(); c->bounds.release(); c->buckets.release(); c->fallback.release(); c->strip_scratch.release(); c->counters.release();
   c->small.release(); c->hits[0].release(); c->hits[1].release(); c->hit_cnt[0].release();
   c->hit_cnt[1].release(); c->jobs.release(); c->big_scratch.release(); c->tb_work.release(); c->chunk_tab.release();
   for (auto &e : c->ev) cudaEventDestroy(e);
@@ -892,16 +885,8 @@ extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *s
     }
     p.strip_scratch = c->strip_scratch.p;
     if (int r = scan_counts(c, first, end, 1, nullptr)) return r;
-    {
-      uint64_t n_cand = 0;
-      for (uint32_t q = first; q < end; ++q) n_cand += c->h_counts[q];
-      GM_CUDA(c->half_query.ensure(n_cand / kSwCandPerTask + (end - first) + 1));
-      half_table_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->prefix.p, end - first, c->half_query.p);
-      GM_CUDA(cudaGetLastError());
-      p.half_query = c->half_query.p;
-    }
     GM_CUDA(sw_extend_launch(p, rows, c->sm_count, c->stream));
-    launches = 3;
+    launches = 2;
   } else {
     GM_CUDA(sw_extend_s32_launch(p, c->sm_count, c->stream));
     launches = 1;

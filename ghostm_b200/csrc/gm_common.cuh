@@ -30,7 +30,6 @@ struct SwParams {
   uint32_t first_query;        // tasks cover queries [first_query, first_query + n_q)
   uint32_t n_q;
   const uint32_t *task_prefix; // [n_q + 1] exclusive prefix of ceil(cnt/32): half tasks per query
-  const uint32_t *half_query;  // [task_prefix[n_q]] half task -> query index (relative to first_query)
   const uint32_t *cand_off;    // [n_queries] first candidate of each query in cand_* arrays
   const uint32_t *cand_cnt;    // [n_queries]
   const uint32_t *cand_start;  // candidate db offsets (region starts)

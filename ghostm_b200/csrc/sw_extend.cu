@@ -70,8 +70,12 @@ __global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_k
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint32_t ht = 2 * task + h;
+      uint32_t lo = 0, hi = p.n_q;  // task_prefix[lo] <= ht < task_prefix[hi]
       if (ht < total_half) {
-        const uint32_t lo = p.half_query[ht];     // one load instead of a binary search of the prefix
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (p.task_prefix[mid] <= ht) lo = mid; else hi = mid;
+        }
         qh[h] = p.first_query + lo;
         blkh[h] = ht - p.task_prefix[lo];
       } else {
