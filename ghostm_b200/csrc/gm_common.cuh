@@ -18,8 +18,7 @@ constexpr uint32_t kNoId = 0xFFFFFFFFu;
 // ---- SW extension ---------------------------------------------------------------------
 constexpr int kSwThreads = 256;          // 8 warps per CTA, one CTA per SM (register bound)
 constexpr int kSwWarps = kSwThreads / 32;
-constexpr int kSwCandPerTask = 32;       // scan granularity: a HALF task = 32 candidates of ONE query;
-                                         // a warp task = two half tasks (low / high s16 halves of the lanes)
+constexpr int kSwCandPerTask = 64;       // one warp task = 64 candidates of ONE query (2 per lane)
 constexpr int kSwMaxRows = 80;           // rows (query residues) held in registers per strip
 
 struct SwParams {
@@ -29,7 +28,7 @@ struct SwParams {
   uint32_t query_len;
   uint32_t first_query;        // tasks cover queries [first_query, first_query + n_q)
   uint32_t n_q;
-  const uint32_t *task_prefix; // [n_q + 1] exclusive prefix of ceil(cnt/32): half tasks per query
+  const uint32_t *task_prefix; // [n_q + 1] exclusive prefix of ceil(cnt/64)
   const uint32_t *cand_off;    // [n_queries] first candidate of each query in cand_* arrays
   const uint32_t *cand_cnt;    // [n_queries]
   const uint32_t *cand_start;  // candidate db offsets (region starts)

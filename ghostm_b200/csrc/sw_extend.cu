@@ -13,10 +13,8 @@
 //  * per cell (x2 candidates) 6 ALU-pipe DPX ops: VIADDMNMX.S16x2 (x4, one with .RELU),
 //    VIADD.16x2, VIMNMX.S16x2; the vertical (F) recurrence is restated so that its loop-carried
 //    dependency is ONE VIADDMNMX per row.
-//  * one warp task = two half tasks of 32 candidates of one query each (low / high halves of the
-//    lanes, usually the same query; at a query's tail the high halves start the next query, so
-//    at most 31 lanes-halves per query idle), the query profile T[row][db residue] (16-bit, in
-//    shared memory, per warp and half) is read at bank = residue: conflict free, and the two
+//  * one warp task = 64 candidates of one query, so the query profile T[row][db residue]
+//    (16-bit, in shared memory, per warp) is read at bank = residue: conflict free, and the two
 //    halves are packed with one IMAD (FMA pipe), off the ALU pipe that bounds the kernel.
 //  * SEQUENCE_END columns and clipped windows are handled by a warp-uniform slow path that
 //    masks the affected half; queries longer than R rows run as horizontal strips whose
@@ -38,10 +36,9 @@ template <int R>
 __global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_kernel(const SwParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int16_t *matT = reinterpret_cast<int16_t *>(smem_raw);                 // [query residue][db residue]
-  uint16_t *prof_all = reinterpret_cast<uint16_t *>(smem_raw + 2048);    // per warp 2 x [R][32]
+  uint16_t *prof_all = reinterpret_cast<uint16_t *>(smem_raw + 2048);    // per warp [R][32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint16_t *profA = prof_all + warp * (2 * R * 32);                      // profile of the low halves' query
-  uint16_t *profB2 = profA + R * 32;                                     // ... of the high halves' query, if different
+  uint16_t *prof = prof_all + warp * (R * 32);
 
   for (int i = threadIdx.x; i < kAlphabet * kAlphabet; i += blockDim.x) {
     const int c = i >> 5, q = i & 31;  // matrix[db residue * 32 + query residue] (aligner.cpp:612-618)
@@ -52,8 +49,7 @@ __global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_k
   const int go = p.open_gap, ge = p.extend_gap;
   const int gef = go > ge ? go : ge;  // F_{k+1} = max(F_k + max(ge,go), m_k + go), see header
   const uint32_t go_pk = pack2(go), ge_pk = pack2(ge), gef_pk = pack2(gef);
-  const uint32_t total_half = p.task_prefix[p.n_q];
-  const uint32_t total_tasks = (total_half + 1) / 2;
+  const uint32_t total_tasks = p.task_prefix[p.n_q];
   const uint32_t gwarp = blockIdx.x * kSwWarps + warp;
   const uint32_t L = p.query_len;
 
@@ -62,45 +58,26 @@ __global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_k
     if (lane == 0) task = atomicAdd(p.task_counter, 1u);
     task = __shfl_sync(kFull, task, 0);
     if (task >= total_tasks) break;
-    // Two half tasks (32 candidates of one query each): the low s16 halves of the lanes take half
-    // task 2*task, the high halves 2*task+1 - usually the next 32 candidates of the same query,
-    // at a query's tail the first 32 of the next one (its own profile), so that only the last
-    // half task of a query can be partly empty.
-    uint32_t qh[2], blkh[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t ht = 2 * task + h;
-      uint32_t lo = 0, hi = p.n_q;  // task_prefix[lo] <= ht < task_prefix[hi]
-      if (ht < total_half) {
-        while (hi - lo > 1) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (p.task_prefix[mid] <= ht) lo = mid; else hi = mid;
-        }
-        qh[h] = p.first_query + lo;
-        blkh[h] = ht - p.task_prefix[lo];
-      } else {
-        qh[h] = kNoId;
-        blkh[h] = 0;
-      }
+    uint32_t lo = 0, hi = p.n_q;  // task_prefix[lo] <= task < task_prefix[hi]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (p.task_prefix[mid] <= task) lo = mid; else hi = mid;
     }
-    const uint32_t qa = qh[0], qb = qh[1];
-    const bool same = qa == qb;
-    const uint8_t *queryA = p.queries + (size_t)qa * L;
-    const uint8_t *queryB = p.queries + (size_t)(qb == kNoId ? qa : qb) * L;
-    const uint16_t *profB = same || qb == kNoId ? profA : profB2;
+    const uint32_t q = p.first_query + lo;
+    const uint32_t blk = task - p.task_prefix[lo];
+    const uint32_t cnt = p.cand_cnt[q], off = p.cand_off[q];
+    const uint8_t *query = p.queries + (size_t)q * L;
 
     // the two candidates of this lane
-    const uint32_t ia = blkh[0] * kSwCandPerTask + lane, ib = blkh[1] * kSwCandPerTask + lane;
-    const uint32_t cnta = p.cand_cnt[qa], offqa = p.cand_off[qa];
-    const uint32_t cntb = qb == kNoId ? 0u : p.cand_cnt[qb], offqb = qb == kNoId ? 0u : p.cand_off[qb];
+    const uint32_t ia = blk * kSwCandPerTask + lane, ib = ia + 32;
     uint32_t wa = 0, wb = 0, offa = 0, offb = 0;
-    if (ia < cnta) {
-      const uint32_t st = p.cand_start[offqa + ia];
+    if (ia < cnt) {
+      const uint32_t st = p.cand_start[off + ia];
       offa = st >= p.extend ? st - p.extend : 0u;                       // aligner.cpp:576-579
       wa = min(p.base_len, p.db_len - offa);                            // aligner.cpp:580-583
     }
-    if (ib < cntb) {
-      const uint32_t st = p.cand_start[offqb + ib];
+    if (ib < cnt) {
+      const uint32_t st = p.cand_start[off + ib];
       offb = st >= p.extend ? st - p.extend : 0u;
       wb = min(p.base_len, p.db_len - offb);
     }
@@ -111,18 +88,14 @@ __global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_k
     uint32_t enda = 0, endb = 0;     // column of the last maximum (aligner.cpp:650-653)
 
     for (uint32_t strip = 0; strip < p.n_strips; ++strip) {
-      // ---- per-warp query profiles of this strip: T[k][c] = matrix[c][query[row]] - open
+      // ---- per-warp query profile of this strip: T[k][c] = matrix[c][query[row]] - open
       __syncwarp();
 #pragma unroll 4
       for (int k = 0; k < R; ++k) {
         const uint32_t row = strip * R + k;
-        int va = -16384 - go, vb = -16384 - go;  // padding rows below the query never score
-        if (row < L) {
-          va = (int)matT[(int)queryA[row] * 32 + lane] - go;
-          vb = (int)matT[(int)queryB[row] * 32 + lane] - go;
-        }
-        profA[k * 32 + lane] = (uint16_t)va;
-        if (!same) profB2[k * 32 + lane] = (uint16_t)vb;
+        int v = -16384 - go;  // padding rows below the query never score
+        if (row < L) v = (int)matT[(int)query[row] * 32 + lane] - go;
+        prof[k * 32 + lane] = (uint16_t)v;
       }
       __syncwarp();
 
@@ -145,7 +118,7 @@ __global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_k
           f = scr[(j * 3 + 1) * 32];
           cmax = scr[(j * 3 + 2) * 32];
         }
-        const uint16_t *ta = profA + ca, *tb = profB + cb;
+        const uint16_t *ta = prof + ca, *tb = prof + cb;
         // Row k+1's insertion/diagonal part is issued before row k's H is written, so that the
         // previous column's H+open of row k is dead by then and hgo[k] is updated in place
         // (no register rotation at the loop back-edge).
@@ -192,13 +165,13 @@ __global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_k
         cb = nb;
       }
     }
-    if (ia < cnta) {
-      p.cand_score[offqa + ia] = (uint32_t)((int)(int16_t)(best & 0xFFFFu) - go);
-      p.cand_end[offqa + ia] = offa + enda;
+    if (ia < cnt) {
+      p.cand_score[off + ia] = (uint32_t)((int)(int16_t)(best & 0xFFFFu) - go);
+      p.cand_end[off + ia] = offa + enda;
     }
-    if (ib < cntb) {
-      p.cand_score[offqb + ib] = (uint32_t)((int)(int16_t)(best >> 16) - go);
-      p.cand_end[offqb + ib] = offb + endb;
+    if (ib < cnt) {
+      p.cand_score[off + ib] = (uint32_t)((int)(int16_t)(best >> 16) - go);
+      p.cand_end[off + ib] = offb + endb;
     }
     const unsigned long long cells =
         (unsigned long long)__reduce_add_sync(kFull, wa + wb) * (unsigned long long)L;
@@ -250,7 +223,7 @@ __global__ void __launch_bounds__(128) sw_extend_s32_kernel(const SwParams p) {
 
 template <int R>
 cudaError_t launch_dpx(const SwParams &p, int sm_count, cudaStream_t stream) {
-  const size_t smem = 2048 + (size_t)kSwWarps * 2 * R * 32 * sizeof(uint16_t);   // two profiles per warp
+  const size_t smem = 2048 + (size_t)kSwWarps * R * 32 * sizeof(uint16_t);
   cudaError_t err = cudaFuncSetAttribute(sw_extend_dpx_kernel<R>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
