@@ -153,3 +153,56 @@ def test_shard_over_nccl_all_visible_gpus(tmp_path):
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     assert out.stdout.count("SHARD_GPU_OK") == 2 * n
+
+
+@pytest.mark.parametrize("name,world", [("small", 2), ("repeats", 3)])
+def test_candidates_transfer_between_contexts(name, world):
+    """gm_candidates_transfer (pack + peer copy + import in one call, the C++ driver's multi-device
+    exchange): per slice the same hit lists as the oracle's single-process run."""
+    from ghostm_b200 import capi, shard
+    db, qchunks, kw = H.workload(name)
+    opt = O.Options(**kw)
+    qc = qchunks[0]
+    ref = O.align_chunk(qc, db, opt)
+    bounds = shard.slice_bounds(qc.name_breaks(), qc.n, world)
+    front_ctx = capi.Context(0)
+    H.setup_context(front_ctx, db, opt)
+    front_ctx.query_upload(qc.seqs, qc.name_breaks())
+    front = shard.GpuFront(front_ctx, qc.n, 1 << 22, "cuda:0")
+    backs = []
+    for r in range(world):
+        base, stop = int(bounds[r]), int(bounds[r + 1])
+        ctx = capi.Context(0)
+        ctx.set_options(db.seed, opt.matrix, shift=opt.shift, log_region=opt.log_region,
+                        threshold=opt.threshold, extend=opt.extend, best=opt.best,
+                        max_list_length=opt.max_list_length, open_gap=opt.open_gap,
+                        extend_gap=opt.extend_gap)
+        ctx.set_candidate_capacity(1 << 22)
+        for i, ch in enumerate(db.chunks):
+            ctx.db_upload_seq(i, ch.seq, ch.seq_starts)
+        sl = H.slice_query_chunk(qc, base, stop)
+        ctx.query_upload(sl.seqs, sl.name_breaks())
+        backs.append(ctx)
+    for c in range(len(db.chunks)):
+        segs = front.prepare(c)
+        if not segs:
+            continue
+        for r, ctx in enumerate(backs):
+            base, stop = int(bounds[r]), int(bounds[r + 1])
+            front_ctx.candidates_transfer_to(ctx, c, base, stop)
+            for f, e in segs:
+                f2, e2 = min(max(f, base), stop), max(min(e, stop), base)
+                if f2 >= e2:
+                    f2 = e2 = base
+                ctx.merge(f2 - base, e2 - base)
+    for r, ctx in enumerate(backs):
+        base, stop = int(bounds[r]), int(bounds[r + 1])
+        hits, counts = ctx.results()
+        assert np.array_equal(counts, ref.counts[base:stop])
+        for i in range(base, stop):
+            got = hits[i - base, :counts[i - base]].copy()
+            got["query_id"] += base
+            ok, field = H.hits_equal(got, ref.hits[i, :ref.counts[i]])
+            assert ok, (name, r, i, field)
+        ctx.close()
+    front_ctx.close()
