@@ -519,6 +519,7 @@ extern "C" int gm_query_upload(gm_context *c, const uint8_t *seqs, uint32_t n, u
   c->cur_chunk = -1;
   c->cand_total = 0;
   c->pending = false;
+  c->imported = false;
   return 0;
 }
 
