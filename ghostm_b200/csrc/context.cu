@@ -34,6 +34,7 @@ int traceback_grid(int sm_count);
 int traceback_threads();
 cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_t stream, bool fast);
 bool traceback_fast_ok(uint32_t query_len, int open_gap, int extend_gap);
+bool traceback_warp_ok(uint32_t query_len, int open_gap, int extend_gap);
 cudaError_t collect_pending_launch(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
                                    uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
                                    uint32_t *n_jobs, int sm_count, cudaStream_t stream);
@@ -957,8 +958,12 @@ int run_traceback(gm_context *c, gm_hit *hits) {
   t.extend_gap = c->opt.extend_gap;
   t.base_len = c->query_len + 2 * c->opt.extend * 2 * (1u << c->opt.log_region);  // aligner.cpp:775
   // the score range check of the packed SW kernel also covers the 16-bit H of this one
+  // (register kernel for L <= 80, warp-cooperative kernel up to L = 1024, else / variant 0 the
+  // generic one-thread-per-hit kernel with its global column scratch)
   const bool fast = c->traceback_fast && !c->use_s32 &&
-                    traceback_fast_ok(c->query_len, c->opt.open_gap, c->opt.extend_gap);
+                    (traceback_fast_ok(c->query_len, c->opt.open_gap, c->opt.extend_gap) ||
+                     (traceback_warp_ok(c->query_len, c->opt.open_gap, c->opt.extend_gap) &&
+                      t.base_len < (1u << 20)));
   if (!fast) {
     const size_t tb_threads = (size_t)traceback_grid(c->sm_count) * traceback_threads();
     GM_CUDA(c->tb_work.ensure(tb_threads * 4 * (c->query_len + 1)));

@@ -549,6 +549,122 @@ __global__ void __launch_bounds__(128, 2) traceback_reg_kernel(const TracebackPa
   }
 }
 
+// Warp-cooperative TraceBack for long queries (80 < L <= 1024; config 4): one WARP per hit, the
+// query rows are split over the lanes in processing order (i = L-1-k: lane l owns rows
+// i in [l*RL, (l+1)*RL)), the reverse DP runs as a systolic wavefront: at step t lane l computes
+// its rows of column j = t - l and hands its last row (H, payload, running deletion) to lane l+1,
+// which is one column behind; the column state of a lane's rows stays in registers ((H<<16|E) and
+// (matches<<16|length) per row).  The db residue of a column travels down the lanes with the
+// wavefront.  Every lane keeps the first strict maximum of its own cells in scan order; the warp
+// then takes the largest score and, among equals, the earliest (column, row) - exactly the cell
+// the sequential scan (aligner.cpp:898) keeps.  One thread per hit needs L+1 columns of global
+// scratch at these lengths and ran 234 ms for 480 hits of 1000 residues.
+template <int RL>
+__global__ void __launch_bounds__(256) traceback_warp_kernel(const TracebackParams p) {
+  __shared__ int16_t mat[kAlphabet * kAlphabet];
+  for (int i = threadIdx.x; i < kAlphabet * kAlphabet; i += blockDim.x) mat[i] = (int16_t)p.matrix[i];
+  __syncthreads();
+  const uint32_t n_jobs = *p.n_jobs;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int L = (int)p.query_len;
+  const int go = p.open_gap, ge = p.extend_gap;
+  for (uint32_t job = gwarp; job < n_jobs; job += n_warps) {
+    gm_hit h = p.hits[p.jobs[job]];
+    const ChunkRef chunk = p.chunks[h.db_chunk];
+    const uint8_t *query = p.queries + (size_t)h.query_id * L;
+    const uint32_t db_offset = h.db_end;
+    uint32_t len = p.base_len;
+    if (db_offset < len) len = db_offset + 1;                         // aligner.cpp:802-805
+    uint32_t qk[RL], he[RL], pay[RL];
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+      const int i = (int)lane * RL + r;
+      qk[r] = i < L ? query[L - 1 - i] : 0xFFu;                       // 0xFF: no such row
+      he[r] = 0;
+      pay[r] = 0;
+    }
+    int best = 0;
+    uint32_t best_j = 0, best_i = 0, best_pay = 0;
+    int out_h = 0, out_del = 0, diag_h = 0;       // last row of this lane / boundary of the previous column
+    uint32_t out_pay = 0, diag_pay = 0;
+    uint32_t cbuf = kSeqEnd, c_cur = kSeqEnd;
+    bool stopped = false;
+    const uint32_t steps = len + 31;
+    for (uint32_t t = 0; t < steps; ++t) {
+      if ((t & 31) == 0) {                                            // next 32 columns, one per lane
+        const uint32_t idx = t + lane;
+        cbuf = idx < len ? chunk.seq[db_offset - idx] : (uint32_t)kSeqEnd;
+      }
+      const uint32_t c0 = __shfl_sync(kFull, cbuf, t & 31);
+      c_cur = __shfl_up_sync(kFull, c_cur, 1);
+      if (lane == 0) c_cur = c0;
+      int in_h = __shfl_up_sync(kFull, out_h, 1), in_del = __shfl_up_sync(kFull, out_del, 1);
+      uint32_t in_pay = __shfl_up_sync(kFull, out_pay, 1);
+      if (lane == 0) { in_h = 0; in_del = 0; in_pay = 0; }            // below row L-1: zeros (:791-797)
+      const uint32_t j = t - lane;
+      bool active = t >= lane && j < len && !stopped;
+      if (active && c_cur == kSeqEnd) { stopped = true; active = false; }   // aligner.cpp:927-929
+      if (active) {
+        const uint32_t c = c_cur;
+        const int16_t *row = mat + c * kAlphabet;
+        int temp_score = diag_h, below_h = in_h, del = in_del;
+        uint32_t temp_pay = diag_pay, below_pay = in_pay;
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          if (qk[r] != 0xFFu) {
+            const uint32_t old = he[r], old_pay = pay[r];
+            const int old_h = (int)old >> 16;
+            int ins = (int)(int16_t)(old & 0xFFFFu);
+            const int s = temp_score + row[qk[r]];
+            int local = 0;
+            uint32_t np = 0;
+            if (s > 0) { local = s; np = temp_pay + (c == qk[r] ? 0x10001u : 0x1u); }
+            ins = max(ins + ge, old_h + go);
+            if (ins > local) { local = ins; np = old_pay + 1; }
+            del = max(del + ge, below_h + go);
+            if (del > local) { local = del; np = below_pay + 1; }
+            temp_score = old_h;
+            temp_pay = old_pay;
+            he[r] = ((uint32_t)local << 16) | ((uint32_t)ins & 0xFFFFu);
+            pay[r] = np;
+            below_h = local;
+            below_pay = np;
+            if (local > best) { best = local; best_j = j; best_i = lane * RL + r; best_pay = np; }  // first max
+          }
+        }
+        out_h = below_h;
+        out_pay = below_pay;
+        out_del = del;
+      }
+      diag_h = in_h;          // boundary of column j becomes the diagonal of column j+1
+      diag_pay = in_pay;
+    }
+    // largest score; among equals the earliest cell in scan order (column, then row)
+    unsigned long long key = ((unsigned long long)(uint32_t)best << 32) |
+                             (0xFFFFFFFFu - ((best_j << 11) | best_i));
+    uint32_t bp = best_pay;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long k2 = __shfl_xor_sync(kFull, key, o);
+      const uint32_t p2 = __shfl_xor_sync(kFull, bp, o);
+      if (k2 > key) { key = k2; bp = p2; }
+    }
+    if (lane == 0) {
+      const uint32_t max_start = (0xFFFFFFFFu - (uint32_t)key) >> 11;
+      const uint32_t seq_pos = chunk.seq_starts[h.db_id];
+      const uint32_t max_match = bp >> 16, max_len = bp & 0xFFFFu;
+      h.db_start = db_offset - max_start - seq_pos;                   // aligner.cpp:941, :715
+      h.db_end = db_offset - seq_pos;                                 // :716
+      h.seq_id = (float)max_match / (float)(int)max_len;              // :945
+      h.aln_len = max_len;
+      h.aln_match = max_match;
+      p.hits[p.jobs[job]] = h;
+    }
+    __syncwarp();
+  }
+}
+
 // Collect the result slots whose TraceBack is pending and whose db chunk is resident here.
 __global__ void collect_pending_kernel(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
                                        uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
@@ -592,7 +708,21 @@ bool traceback_fast_ok(uint32_t query_len, int open_gap, int extend_gap) {
   return query_len <= 80 && open_gap > -8000 && extend_gap > -8000 && open_gap <= 0 && extend_gap <= 0;
 }
 
+// True when the warp-cooperative kernel covers this query length and gap/score range (16-bit H, E).
+bool traceback_warp_ok(uint32_t query_len, int open_gap, int extend_gap) {
+  return query_len <= 1024 && open_gap > -8000 && extend_gap > -8000 && open_gap <= 0 && extend_gap <= 0;
+}
+
 cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_t stream, bool fast) {
+  if (fast && !traceback_fast_ok(p.query_len, p.open_gap, p.extend_gap) &&
+      traceback_warp_ok(p.query_len, p.open_gap, p.extend_gap) && p.base_len < (1u << 20)) {
+    const int grid = sm_count * 4;
+    if (p.query_len <= 128) traceback_warp_kernel<4><<<grid, 256, 0, stream>>>(p);
+    else if (p.query_len <= 256) traceback_warp_kernel<8><<<grid, 256, 0, stream>>>(p);
+    else if (p.query_len <= 512) traceback_warp_kernel<16><<<grid, 256, 0, stream>>>(p);
+    else traceback_warp_kernel<32><<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
   if (fast && traceback_fast_ok(p.query_len, p.open_gap, p.extend_gap)) {
     const int grid = sm_count * 2;
     if (p.query_len <= 32) traceback_reg_kernel<32><<<grid, 128, 0, stream>>>(p);

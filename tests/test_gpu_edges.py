@@ -117,3 +117,14 @@ def test_capacity_error_is_loud(gpu_ctx):
         gpu_ctx.align_chunk(0)
     with pytest.raises(capi.GhostmError, match="threshold"):
         gpu_ctx.set_options(db.seed, opt.matrix, threshold=5)
+
+
+@pytest.mark.parametrize("length", [81, 100, 128, 200, 257, 520])
+def test_query_lengths_across_the_traceback_kernels(gpu_ctx, length):
+    """L <= 80: register TraceBack; above: the warp-cooperative wavefront kernel with 4 / 8 / 16 / 32
+    rows per lane (and strip-mined SW, generic seed search once list_len > 64)."""
+    dbs, dbn = _small_db(17, 80_000)
+    qs, qn = synth.queries_from_db(18, dbs, 40, length, group=2, min_length=length // 2)
+    db = formats.make_db(dbs, dbn, 4, 1)
+    qc = formats.make_query_chunks(qs, qn, length, 128)[0]
+    assert _check(gpu_ctx, db, qc, O.Options()) > 0
