@@ -652,7 +652,6 @@ constexpr int kBkLists = 64;
 constexpr int kBkUnroll = 4;            // chunks per batch in phase A (two batches in flight)
 constexpr int kBkEmitCap = 126;         // emitted regions per tile (u16 list, 64 words with its counter)
 constexpr uint32_t kBkEmpty = 0x7FFFFFFFu;   // empty register slot: bit 31 (owner) clear, no valid region
-constexpr uint32_t kBkMaxTileBits = 15;
 constexpr uint32_t kBkMinTileBits = 10;
 
 struct BucketShared {
@@ -1056,8 +1055,7 @@ __global__ void __launch_bounds__(kHsThreads, 1) seed_search_hash_kernel(const S
   uint32_t *coll = dyn + kHsOccWords;        // [kHsCollWords]  passes 1-2: collisions; 4: range buckets
   uint32_t *susp = coll + kHsCollWords;      // [kHsSuspCap]
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t r = p.log_region, hmask = kHsOccBits - 1;
-  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t r = p.log_region;
   // range bucket of a region: monotone in d, 32 buckets over [0, n_regions)
   uint32_t bshift = 0;
   while ((p.n_regions >> bshift) > kHsBuckets) ++bshift;
