@@ -15,6 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libghostm_b200.so")
 
+DEFAULT_SEARCH_VARIANT = 4
+
 LEGACY_SYMBOLS = ["InitGpu", "GetNeededGPUMemorySize", "CheckGpuMemory", "SetOptionGpu",
                   "printGpuInfo", "SetQueryGpu", "SetDbGpu", "SearchNextGpu", "CalculateScoreGpu",
                   "FreeGpu"]
@@ -275,7 +277,8 @@ class Context:
         return hits, counts
 
     def set_search_variant(self, variant: int):
-        """2 = bucket kernel (default), 3 = hash kernel, 1 = sweep kernel, 0 = generic kernels."""
+        """4 = tile kernel (default), 2 = bucket kernel, 3 = hash kernel, 1 = sweep kernel,
+        0 = generic kernels."""
         self._check(self.L.gm_set_search_variant(self.h, int(variant)))
 
     def set_deferred_traceback(self, on: bool):

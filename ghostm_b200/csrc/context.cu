@@ -26,6 +26,13 @@ int search_bucket_grid(int sm_count);
 bool search_hash_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions);
 cudaError_t seed_search_hash_launch(const SearchParams &p, int sm_count, cudaStream_t stream);
 cudaError_t seed_search_bucket_launch(const SearchParams &p, int sm_count, cudaStream_t stream);
+bool search_tile_geometry(uint32_t threshold, uint32_t list_len, uint32_t shift, uint32_t log_region,
+                          uint32_t seq_len, uint32_t n_keys, TileGeometry *g);
+int search_tile_grid(int sm_count);
+cudaError_t search_split_build(const uint32_t *keys_count, uint32_t n_keys, const uint32_t *positions,
+                               const TileGeometry &g, uint32_t *split, int sm_count, cudaStream_t stream);
+cudaError_t seed_search_tile_launch(SearchParams p, const TileGeometry &g, int sm_count,
+                                    cudaStream_t stream);
 int search_max_list_len();
 int search_max_threshold();
 size_t merge_smem_bytes(uint32_t elems_per_warp);
@@ -203,6 +210,10 @@ struct DbChunk {
   uint32_t seq_len = 0, keys_count_len = 0, positions_len = 0, n_seqs = 0;
   bool valid = false;
   bool has_index = false;   // false: sequence-only chunk (gm_db_upload_seq), Merge/TraceBack side
+  // tiled seed search: per-key tile boundaries inside positions[], built on first use
+  DevBuf<uint32_t> split;
+  TileGeometry split_geom = {};
+  bool split_valid = false;
 };
 
 }  // namespace
@@ -262,6 +273,7 @@ struct gm_context {
   bool search_fast = true;   // balanced register-resident search kernel when the options allow it
   bool search_bucket = true; // bucket kernel (threshold 2) in front of it
   bool search_hash = false;  // hash kernel (threshold 2) instead of the bucket kernel: variant 3 only
+  bool search_tile = true;   // tile kernel (threshold 2) in front of all of them: variant 4, the default
   bool traceback_fast = true;
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits
@@ -359,6 +371,7 @@ extern "C" void gm_destroy(gm_context *c) {
   cudaStreamSynchronize(c->stream);
   for (auto &ch : c->chunks) {
     ch.seq.release(); ch.keys_count.release(); ch.positions.release(); ch.seq_starts.release();
+    ch.split.release();
   }
   c->matrix.release(); c->queries.release(); c->run_first.release(); c->run_last.release();
   c->cand_off.release(); c->cand_cnt.release(); c->cand_start.release(); c->cand_score.release();
@@ -438,6 +451,7 @@ extern "C" int gm_db_upload(gm_context *c, uint32_t id, const uint8_t *seq, uint
   ch.n_seqs = n_seqs;
   ch.valid = true;
   ch.has_index = true;
+  ch.split_valid = false;
   c->chunk_tab_dirty = true;
   if (c->cur_chunk == (int)id) c->cur_chunk = -1;
   return 0;
@@ -452,6 +466,8 @@ extern "C" int gm_db_upload_seq(gm_context *c, uint32_t id, const uint8_t *seq, 
   ch.valid = false;
   ch.keys_count.release();
   ch.positions.release();
+  ch.split.release();
+  ch.split_valid = false;
   GM_CUDA(ch.seq.ensure(seq_len));
   GM_CUDA(ch.seq_starts.ensure(n_seqs));
   GM_CUDA(cudaMemcpyAsync(ch.seq.p, seq, seq_len, cudaMemcpyHostToDevice, c->stream));
@@ -475,6 +491,8 @@ extern "C" int gm_db_release(gm_context *c, uint32_t id) {
   DbChunk &ch = c->chunks[id];
   GM_CUDA(cudaStreamSynchronize(c->stream));
   ch.seq.release(); ch.keys_count.release(); ch.positions.release(); ch.seq_starts.release();
+  ch.split.release();
+  ch.split_valid = false;
   ch.valid = false;
   c->chunk_tab_dirty = true;
   if (c->cur_chunk == (int)id) c->cur_chunk = -1;
@@ -573,9 +591,29 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     p.positions_visited = c->counters.p + 1;
     p.overflow = reinterpret_cast<int *>(c->small.p + 2);
     uint32_t tile_bits = 0, bucket_cap = 0, launches = 1;
-    const bool hash = c->search_hash && c->search_fast &&
+    TileGeometry tg = {};
+    const bool tile = c->search_tile && c->search_fast && ch.keys_count_len > 1 &&
+                      search_tile_geometry(p.threshold, p.list_len, p.shift, p.log_region, ch.seq_len,
+                                           ch.keys_count_len - 1, &tg);
+    if (tile) {
+      if (!ch.split_valid || memcmp(&ch.split_geom, &tg, sizeof(tg)) != 0) {
+        ch.split_valid = false;
+        GM_CUDA(ch.split.ensure((size_t)(ch.keys_count_len - 1) * tg.n_tiles + 1));
+        GM_CUDA(search_split_build(ch.keys_count.p, ch.keys_count_len - 1, ch.positions.p, tg,
+                                   ch.split.p, c->sm_count, c->stream));
+        ch.split_geom = tg;
+        ch.split_valid = true;
+      }
+      GM_CUDA(c->staging.ensure((size_t)search_tile_grid(c->sm_count) * c->staging_cap));
+      p.staging = c->staging.p;
+      GM_CUDA(c->fallback.ensure(c->n_queries));
+      p.split = ch.split.p;
+      p.fallback_list = c->fallback.p;
+      p.fallback_n = c->small.p + 6;
+    }
+    const bool hash = !tile && c->search_hash && c->search_fast &&
                       search_hash_ok(p.threshold, p.list_len, p.n_regions);
-    const bool bucket = !hash && c->search_bucket && c->search_fast &&
+    const bool bucket = !tile && !hash && c->search_bucket && c->search_fast &&
                         search_bucket_ok(p.threshold, p.list_len, p.n_regions, &tile_bits, &bucket_cap);
     if (hash) {
       GM_CUDA(c->fallback.ensure(c->n_queries));
@@ -596,12 +634,14 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
       p.fallback_n = c->small.p + 6;
     }
     GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    if (bucket || hash) {
-      if (hash) GM_CUDA(seed_search_hash_launch(p, c->sm_count, c->stream));
+    if (tile || bucket || hash) {
+      if (tile) GM_CUDA(seed_search_tile_launch(p, tg, c->sm_count, c->stream));
+      else if (hash) GM_CUDA(seed_search_hash_launch(p, c->sm_count, c->stream));
       else GM_CUDA(seed_search_bucket_launch(p, c->sm_count, c->stream));
       uint32_t n_fb = 0;
       GM_CUDA(cudaMemcpyAsync(&n_fb, c->small.p + 6, 4, cudaMemcpyDeviceToHost, c->stream));
       GM_CUDA(cudaStreamSynchronize(c->stream));
+      if (getenv("GM_DEBUG_SEARCH")) fprintf(stderr, "[gm_search] %u of %u queries fall back to the sweep kernel\n", n_fb, c->n_queries);
       if (n_fb) {   // queries beyond the bucket kernel's capacities: the sweep kernel, same results
         GM_CUDA(cudaMemsetAsync(c->small.p + 0, 0, 4, c->stream));
         p.query_list = c->fallback.p;
@@ -979,7 +1019,8 @@ extern "C" int gm_set_search_variant(gm_context *c, int fast) {
   if (int r = check_ctx(c)) return r;
   c->search_fast = fast != 0;
   c->search_bucket = fast >= 2;
-  c->search_hash = fast >= 3;
+  c->search_hash = fast == 3;
+  c->search_tile = fast >= 4;
   c->traceback_fast = fast != 0;
   return 0;
 }

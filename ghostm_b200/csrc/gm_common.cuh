@@ -69,6 +69,17 @@ struct SearchParams {
   uint16_t *buckets;           // [gridDim.x][n_tiles][bucket_cap], L2-resident scratch
   uint32_t *fallback_list;     // queries that exceed a capacity, redone by the sweep kernel
   uint32_t *fallback_n;
+  // tile kernel (threshold 2, seed_search_tile.cu)
+  const uint32_t *split;       // [n_keys * tl_tiles + 1] per-key tile boundaries inside positions[]
+  uint32_t tl_nw, tl_hc;       // bitmap words per tile (31 regions each) + carried halo words
+  uint32_t tl_nb, tl_wpb_log;  // range buckets per tile, log2 words per bucket (tl_nw = tl_nb << tl_wpb_log)
+  uint32_t tl_tiles;
+};
+
+// Geometry of the tiled seed search for one db chunk (search_tile_geometry).
+struct TileGeometry {
+  uint32_t nw, hc, nb, wpb_log, n_tiles;
+  uint32_t tile_pos;           // positions per tile: (31 * nw) << log_region
 };
 
 // ---- merge / traceback --------------------------------------------------------------

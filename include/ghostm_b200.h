@@ -185,8 +185,10 @@ int gm_results_upload(gm_context *ctx, const gm_hit *hits, const uint32_t *count
  * context.  gm_results_download calls it implicitly.  on = 0 restores the reference order
  * (TraceBack inside every Merge). */
 int gm_set_deferred_traceback(gm_context *ctx, int on);
-/* Kernel variants: 2 (default) = bucket seed-search kernel when threshold == 2 and
- * list_len <= 64 (queries beyond its capacities are redone by the sweep kernel), else as 1;
+/* Kernel variants: 4 (default) = tiled seed-search kernel (per-key tile boundaries in the index,
+ * one-pass detection in a 31+1-bit occupancy bitmap) when threshold == 2 and list_len <= 64, else
+ * as 2; 2 = bucket seed-search kernel under the same conditions (queries beyond its capacities are
+ * redone by the sweep kernel), else as 1;
  * 3 = hash seed-search kernel under the same conditions (an independent algorithm, ~20 % slower);
  * 1 = balanced register-resident sweep kernel whenever list_len <= 64 and register-resident
  * TraceBack whenever L <= 80, else the generic kernels; 0 = always the generic kernels (tests).

@@ -2,7 +2,7 @@
 
 The oracle cannot run whole configs 3-5 in a test (config 3 is ~36 core-hours), so every case
 combines, on ONE full-size db chunk built on the device:
-  * cross-kernel identity on all queries: the four seed-search kernels (hash, bucket, sweep, generic)
+  * cross-kernel identity on all queries: the five seed-search kernels (tile, hash, bucket, sweep, generic)
     are different algorithms and must agree candidate for candidate;
   * bit-exact comparison with the oracle on a seeded SAMPLE of the queries: candidates, SW
     scores/ends and the final hit lists (queries have unique names, so a query's list depends on
@@ -39,7 +39,7 @@ def _search_all_variants(ctx, n_q, variants):
         else:
             assert np.array_equal(ref[0], counts), f"variant {v}: counts differ"
             assert np.array_equal(ref[1], ids) and np.array_equal(ref[2], cand), f"variant {v}"
-    ctx.set_search_variant(2)
+    ctx.set_search_variant(capi.DEFAULT_SEARCH_VARIANT)
     return ref
 
 
@@ -111,7 +111,7 @@ def test_config3_full_chunk():
     db = _device_chunk(ctx, seq, starts)
     queries = workloads.synth_queries(2, seq[:4 << 20].copy(), n_q, 75)
     ctx.query_upload(queries)
-    counts, ids, cand = _search_all_variants(ctx, n_q, (3, 2, 1, 0))
+    counts, ids, cand = _search_all_variants(ctx, n_q, (4, 3, 2, 1, 0))
     assert counts.mean() > 300
     ctx.align_chunk(0)
     hits, hit_counts = ctx.results()
@@ -135,7 +135,7 @@ def test_config4_long_queries_full_chunk():
     db = _device_chunk(ctx, seq, starts)
     queries = workloads.synth_queries(4, seq[:4 << 20].copy(), n_q, L, frac_db=1.0)
     ctx.query_upload(queries)
-    counts, ids, cand = _search_all_variants(ctx, n_q, (3, 0))
+    counts, ids, cand = _search_all_variants(ctx, n_q, (4, 3, 0))
     ctx.align_chunk(0)
     hits, hit_counts = ctx.results()
     _check_properties(counts, ids, cand, hits, hit_counts, opt.best)
@@ -160,7 +160,7 @@ def test_config5_repeats_full_chunk():
     qs, _ = synth.repeat_queries(6, n_q, 75)
     queries = np.ascontiguousarray(np.stack(qs))
     ctx.query_upload(queries)
-    counts, ids, cand = _search_all_variants(ctx, n_q, (3, 2, 1, 0))
+    counts, ids, cand = _search_all_variants(ctx, n_q, (4, 3, 2, 1, 0))
     ctx.align_chunk(0)
     hits, hit_counts = ctx.results()
     _check_properties(counts, ids, cand, hits, hit_counts, opt.best)

@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+from ghostm_b200 import capi
 from oracle import oracle as O
 from tests import helpers as H
 
@@ -10,11 +11,11 @@ pytestmark = pytest.mark.gpu
 WORKLOADS = ["small", "frames6", "repeats", "long", "options"]
 
 
-@pytest.mark.parametrize("fast_search", [3, 2, 1, 0])
+@pytest.mark.parametrize("fast_search", [4, 3, 2, 1, 0])
 @pytest.mark.parametrize("name", WORKLOADS)
 def test_stage_parity(gpu_ctx, name, fast_search):
     """(query_id, db_start) after search and (score, db_end) after SW, per candidate chunk;
-    all four seed-search kernels (hash, bucket, register-window sweep, generic)."""
+    all five seed-search kernels (tile, hash, bucket, register-window sweep, generic)."""
     db, qchunks, kw = H.workload(name)
     opt = O.Options(**kw)
     H.setup_context(gpu_ctx, db, opt)
@@ -34,10 +35,10 @@ def test_stage_parity(gpu_ctx, name, fast_search):
                 assert np.array_equal(ends, gends), np.flatnonzero(ends != gends)[:10]
                 n_stages += 1
     assert n_stages > 0
-    gpu_ctx.set_search_variant(2)
+    gpu_ctx.set_search_variant(capi.DEFAULT_SEARCH_VARIANT)
 
 
-@pytest.mark.parametrize("deferred,fast", [(True, 3), (True, 2), (False, 1), (False, 0)])
+@pytest.mark.parametrize("deferred,fast", [(True, 4), (True, 3), (True, 2), (False, 1), (False, 0)])
 @pytest.mark.parametrize("name", WORKLOADS)
 def test_hit_lists(gpu_ctx, name, deferred, fast):
     """Final hit lists (Merge + TraceBack on the device), with TraceBack deferred to the
@@ -59,7 +60,7 @@ def test_hit_lists(gpu_ctx, name, deferred, fast):
             assert ok, (name, i, field, hits[i, :counts[i]], ref.hits[i, :counts[i]])
     assert int(ref.counts.sum()) > 0
     gpu_ctx.set_deferred_traceback(True)
-    gpu_ctx.set_search_variant(2)
+    gpu_ctx.set_search_variant(capi.DEFAULT_SEARCH_VARIANT)
 
 
 @pytest.mark.parametrize("name,world", [("small", 3), ("repeats", 2), ("options", 2), ("frames6", 4),
