@@ -250,6 +250,7 @@ struct gm_context {
   uint32_t staging_cap = 1u << 15;
   DevBuf<uint16_t> buckets;           // bucket seed search: [grid][tiles][bucket_cap] marks
   DevBuf<uint32_t> fallback;          // queries the bucket kernel hands to the sweep kernel
+  DevBuf<uint32_t> tile_emap;         // tile seed search: dense-mode emit bitmaps [grid][words]
   DevBuf<uint32_t> prefix;            // scan output (n_queries + 1)
   DevBuf<uint32_t> bounds;            // gm_candidates_pack part boundaries
   DevBuf<uint32_t> gather0, gather1, gather2;
@@ -274,6 +275,7 @@ struct gm_context {
   bool search_bucket = true; // bucket kernel (threshold 2) in front of it
   bool search_hash = false;  // hash kernel (threshold 2) instead of the bucket kernel: variant 3 only
   bool search_tile = true;   // tile kernel (threshold 2) in front of all of them: variant 4, the default
+  int tile_test = 0;         // variants 5, 6: the tile kernel's dense / in-place paths forced (tests)
   bool traceback_fast = true;
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits
@@ -376,7 +378,7 @@ extern "C" void gm_destroy(gm_context *c) {
   c->matrix.release(); c->queries.release(); c->run_first.release(); c->run_last.release();
   c->cand_off.release(); c->cand_cnt.release(); c->cand_start.release(); c->cand_score.release();
   c->cand_end.release(); c->staging.release(); c->prefix.release(); c->gather0.release();
-  c->gather1.release(); c->gather2.release(); c->bounds.release(); c->buckets.release(); c->fallback.release(); c->strip_scratch.release(); c->counters.release();
+  c->gather1.release(); c->gather2.release(); c->bounds.release(); c->buckets.release(); c->fallback.release(); c->tile_emap.release(); c->strip_scratch.release(); c->counters.release();
   c->small.release(); c->hits[0].release(); c->hits[1].release(); c->hit_cnt[0].release();
   c->hit_cnt[1].release(); c->jobs.release(); c->big_scratch.release(); c->tb_work.release(); c->chunk_tab.release();
   for (auto &e : c->ev) cudaEventDestroy(e);
@@ -606,10 +608,16 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
       }
       GM_CUDA(c->staging.ensure((size_t)search_tile_grid(c->sm_count) * c->staging_cap));
       p.staging = c->staging.p;
-      GM_CUDA(c->fallback.ensure(c->n_queries));
+      // dense-mode emit bitmaps, one per CTA; the kernel leaves them all zero
+      const size_t emap_words = (size_t)search_tile_grid(c->sm_count) * ((tg.nw + tg.hc + 3u) & ~3u);
+      if (c->tile_emap.n < emap_words) {
+        GM_CUDA(c->tile_emap.ensure(emap_words));
+        GM_CUDA(cudaMemsetAsync(c->tile_emap.p, 0, emap_words * 4, c->stream));
+      }
       p.split = ch.split.p;
-      p.fallback_list = c->fallback.p;
-      p.fallback_n = c->small.p + 6;
+      p.tl_emap = c->tile_emap.p;
+      p.tl_force_dense = c->tile_test >= 1;
+      if (c->tile_test >= 2) p.staging_cap = 16;
     }
     const bool hash = !tile && c->search_hash && c->search_fast &&
                       search_hash_ok(p.threshold, p.list_len, p.n_regions);
@@ -634,9 +642,10 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
       p.fallback_n = c->small.p + 6;
     }
     GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    if (tile || bucket || hash) {
-      if (tile) GM_CUDA(seed_search_tile_launch(p, tg, c->sm_count, c->stream));
-      else if (hash) GM_CUDA(seed_search_hash_launch(p, c->sm_count, c->stream));
+    if (tile) {   // no capacity anywhere (sparse, dense and in-place attempts inside the kernel)
+      GM_CUDA(seed_search_tile_launch(p, tg, c->sm_count, c->stream));
+    } else if (bucket || hash) {
+      if (hash) GM_CUDA(seed_search_hash_launch(p, c->sm_count, c->stream));
       else GM_CUDA(seed_search_bucket_launch(p, c->sm_count, c->stream));
       uint32_t n_fb = 0;
       GM_CUDA(cudaMemcpyAsync(&n_fb, c->small.p + 6, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1021,6 +1030,7 @@ extern "C" int gm_set_search_variant(gm_context *c, int fast) {
   c->search_bucket = fast >= 2;
   c->search_hash = fast == 3;
   c->search_tile = fast >= 4;
+  c->tile_test = fast >= 5 ? fast - 4 : 0;   // 5: dense mode forced; 6: and a 16-entry staging area
   c->traceback_fast = fast != 0;
   return 0;
 }

@@ -74,6 +74,8 @@ struct SearchParams {
   uint32_t tl_nw, tl_hc;       // bitmap words per tile (31 regions each) + carried halo words
   uint32_t tl_nb, tl_wpb_log;  // range buckets per tile, log2 words per bucket (tl_nw = tl_nb << tl_wpb_log)
   uint32_t tl_tiles;
+  uint32_t tl_force_dense;     // tests: skip the sparse attempt
+  uint32_t *tl_emap;           // [gridDim.x][tl_nw + tl_hc rounded up to 4] dense-mode emit bitmaps, all zero
 };
 
 // Geometry of the tiled seed search for one db chunk (search_tile_geometry).

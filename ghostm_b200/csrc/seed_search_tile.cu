@@ -57,7 +57,8 @@ constexpr uint32_t kTlNone = 0xFFFFFFFFu;
 
 struct TileShared {
   uint32_t lbeg[kTlLists];               // first usable entry of list j (aligner.cpp:430-431)
-  uint32_t query, stage_n, bad, n_steps;
+  uint32_t query, stage_n, bad, n_steps, weight;
+  uint32_t wsum[32];                     // dense mode: per-warp counts of the ordered scan
   unsigned long long base;
   unsigned long long visited;
 };
@@ -103,6 +104,12 @@ __device__ __noinline__ bool tl_emit(uint32_t *e, uint32_t g) {
   return false;
 }
 
+// Dense mode: emitted tile-local region x -> bit of the CTA's emit bitmap (global memory, L2).
+__device__ __noinline__ void tl_emit_dense(uint32_t *emap, uint32_t x) {
+  const uint32_t w = tl_div31(x);
+  atomicOr(emap + w, 1u << (x - 31u * w));
+}
+
 // split[key * n_tiles + T] = lower bound of T * tile_pos in key's position list; one extra entry at
 // the end (= positions_len), so that entry (key, n_tiles) is the end of key's list for every key.
 __global__ void split_build_kernel(const uint32_t *__restrict__ keys_count, uint32_t n_keys,
@@ -140,13 +147,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) seed_search_tile_kernel(const S
   uint32_t *bent = dyn + occ_words + 4 * kTlTabCap;      // [2 * nb][kTlBucketCap] ring of range buckets
   uint32_t *bounds = bent + 2 * nb * kTlBucketCap;       // [list_len][nT + 1] slices of this query
   uint32_t *stage = p.staging + (size_t)blockIdx.x * p.staging_cap;
+  uint32_t *emap = p.tl_emap + (size_t)blockIdx.x * occ_words;   // dense mode: emitted regions of the tile
   uint32_t occ_s = tl_smem_addr(occ);
   asm volatile("mov.u32 %0, %0;" : "+r"(occ_s));   // keep the window address in a register
   const uint32_t *__restrict__ positions = p.positions;
 
   for (uint32_t i = tid; i < 2 * nb * kTlBucketCap; i += kThreads) bent[i] = kTlNone;
-  if (tid == 0) sh.visited = 0;
+  if (tid == 0) { sh.visited = 0; sh.weight = 0; }
   __syncthreads();
+
+  uint32_t *out = stage;            // where the ordered candidates of the current attempt go
+  uint32_t out_cap = p.staging_cap;
 
   // ---- one warp: sort the first n_b buckets of tile T, append them in order to the staging area
   auto finalize = [&](uint32_t T, uint32_t n_b) {
@@ -193,7 +204,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) seed_search_tile_kernel(const S
 #pragma unroll
         for (int i = 0; i < kTlBucketCap; ++i)
           if ((uint32_t)i < cnt) {          // sorted: the entries come first, kTlNone last
-            if (at < p.staging_cap) stage[at] = v[i] << r;
+            if (at < out_cap) out[at] = v[i] << r;
             ++at;
           }
         total += __shfl_sync(kFull, incl, 31);
@@ -255,114 +266,223 @@ __global__ void __launch_bounds__(NW * 32, MINB) seed_search_tile_kernel(const S
       while (b < e1 && positions[b] < off) ++b;                        // aligner.cpp:430-431
       bj[0] = b;
       sh.lbeg[j] = b;
-      if (bj[nT] > b) atomicAdd(&sh.visited, (unsigned long long)(bj[nT] - b));
+      if (bj[nT] > b) {
+        atomicAdd(&sh.visited, (unsigned long long)(bj[nT] - b));
+        atomicAdd(&sh.weight, bj[nT] - b);
+      }
     }
-    if (tid == 0) { sh.stage_n = 0; sh.bad = 0; }
     __syncthreads();
 
-    for (uint32_t T = 0; T < nT; ++T) {
-      // ---- prologue: table of tile T (warp 0), buckets of tile T-1 (warp 1), bitmap (the rest)
-      if (warp == 0) {
-        build_table(T, 0);
-      } else if (warp == 1) {
-        if (T) finalize(T - 1, nb);
-      } else {
-        const uint32_t ct = tid - 64, cn = kThreads - 64;
-        uint4 *o4 = reinterpret_cast<uint4 *>(occ);
-        if (T == 0) {
-#pragma unroll 4
-          for (uint32_t i = ct; i < occ_words / 4; i += cn) o4[i] = make_uint4(0, 0, 0, 0);
+    // Attempt 0 is the sparse path (emissions in range buckets).  A query that overflows a bucket
+    // or the staging area is redone in DENSE mode: emissions become bits of a per-CTA bitmap in
+    // global memory that every tile scans in order - no capacity anywhere; if even the staging
+    // area is too small, a last attempt writes straight into the query's slice of the output.
+    out = stage;
+    out_cap = p.staging_cap;
+    // W marks in R regions emit about 1.5 W^2 / R regions, i.e. 1.5 * 31 * 2^wpb_log * (W / R)^2 per
+    // bucket: beyond ~1.5 per bucket an overflow is likely, so such a query starts in dense mode
+    const float wr = (float)sh.weight / (float)p.n_regions;
+    bool dense = p.tl_force_dense != 0 || wr * wr * (float)(31u << wpb_log) > 1.0f, direct = false;
+    __syncthreads();
+    if (tid == 0) sh.weight = 0;
+    uint32_t n = 0;
+    while (true) {
+      if (tid == 0) { sh.stage_n = 0; sh.bad = 0; }
+      __syncthreads();
+
+      for (uint32_t T = 0; T < nT; ++T) {
+        // ---- prologue: table of tile T (warp 0), buckets of tile T-1 (warp 1), bitmap (the rest)
+        if (warp == 0) {
+          build_table(T, 0);
+        } else if (warp == 1) {
+          if (T && !dense) finalize(T - 1, nb);
         } else {
-          const uint32_t h4 = (hc + 3u) & ~3u;                  // nw % 4 == 0
+          const uint32_t ct = tid - 64, cn = kThreads - 64;
+          uint4 *o4 = reinterpret_cast<uint4 *>(occ);
+          if (T == 0) {
 #pragma unroll 4
-          for (uint32_t i = h4 / 4 + ct; i < nw / 4; i += cn) o4[i] = make_uint4(0, 0, 0, 0);
-          if (ct < h4) {
-            if (ct < hc) {          // carry: the top hc words become the bottom ones
-              const uint32_t v = occ[nw + ct];
-              occ[nw + ct] = 0;
-              occ[ct] = v;
-            } else {
-              occ[ct] = 0;
-            }
-          }
-        }
-      }
-      const uint32_t gbase = T * 31u * nw - 31u * hc;          // global region of local region 0
-      const uint32_t ring = (T & 1u) * nb;
-      for (uint32_t s0 = 0;; s0 += kTlTabCap) {
-        if (s0) {
-          __syncthreads();
-          if (warp == 0) build_table(T, s0);
-        }
-        __syncthreads();   // A
-        const uint32_t S = sh.n_steps;
-        const uint32_t n_round = min(S - s0, (uint32_t)kTlTabCap);
-        // contiguous share of the round's steps for every warp, kTlUnroll loads in flight
-        const uint32_t per = (n_round + NW - 1) / NW;
-        const uint32_t i1 = min(warp * per + per, n_round);
-        for (uint32_t i = warp * per; i < i1; i += kTlUnroll) {
-          const uint32_t cnt = i1 - i;
-          uint32_t pv[kTlUnroll], cj[kTlUnroll];
-#pragma unroll
-          for (int u = 0; u < kTlUnroll; ++u) {
-            if (u == 0 || (uint32_t)u < cnt) {
-              const uint4 ent = tab[i + u];
-              // lanes past the end re-read the last entry (same region as their left neighbour: no
-              // mark); lane 0 without a predecessor gets a region no position can have
-              const uint32_t idx = ent.w + min(ent.x + lane, ent.y - 1u);
-              cj[u] = (lane == 0 && ent.x == kTlNone) ? ent.z ^ 0x80000000u : ent.z;
-              pv[u] = __ldg(positions + idx);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < kTlUnroll; ++u) {
-            if (u == 0 || (uint32_t)u < cnt) {
-              const uint32_t l = (pv[u] - cj[u]) >> r;
-              const uint32_t lp = __shfl_up_sync(kFull, l, 1);   // lane 0 receives its own l: never a mark
-              const bool mark = l != lp;
-              const uint32_t qw = tl_div31(l), b = l - qw * 31u, bit = 1u << b;
-              const uint32_t wa = occ_s + 4u * qw;
-              const uint32_t old = tl_atoms_or(wa, bit, mark);
-              const uint32_t old2 = tl_atoms_or(wa - 4u, 0x80000000u, mark && b == 0);
-              const uint32_t self = old & (3u << b);
-              const uint32_t left = (old & (bit >> 1)) | (old2 & 0x40000000u);
-              if (__any_sync(kFull, (self | left) != 0)) {
-                // up to two emitted regions per mark: l (a second list, or the right neighbour is
-                // occupied) and l - 1 (the left neighbour is occupied; also the virtual region 0 of
-                // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an
-                // unoccupied region 0 still emits when region 1 alone reaches the threshold)
-                const bool lo = left != 0 || (gbase + l == 1u && (old & bit) != 0);
-                if (lo) {
-                  const uint32_t x = l - 1u;
-                  uint32_t slot = ring + (tl_div31(x) >> wpb_log);
-                  if (slot >= 2 * nb) slot -= 2 * nb;
-                  if (!tl_emit(bent + slot * kTlBucketCap, gbase + x)) sh.bad = 1;
+            for (uint32_t i = ct; i < occ_words / 4; i += cn) o4[i] = make_uint4(0, 0, 0, 0);
+          } else {
+            const uint32_t h4 = (hc + 3u) & ~3u;                  // nw % 4 == 0
+#pragma unroll 4
+            for (uint32_t i = h4 / 4 + ct; i < nw / 4; i += cn) o4[i] = make_uint4(0, 0, 0, 0);
+            if (ct < h4) {
+              if (ct < hc) {          // carry: the top hc words become the bottom ones
+                const uint32_t v = occ[nw + ct];
+                occ[nw + ct] = 0;
+                occ[ct] = v;
+                if (dense) {
+                  const uint32_t ev = __ldcg(emap + nw + ct);
+                  emap[nw + ct] = 0;
+                  emap[ct] = ev;
                 }
-                if (self) {
-                  uint32_t slot = ring + (qw >> wpb_log);
-                  if (slot >= 2 * nb) slot -= 2 * nb;
-                  if (!tl_emit(bent + slot * kTlBucketCap, gbase + l)) sh.bad = 1;
-                }
+              } else {
+                occ[ct] = 0;
               }
             }
           }
         }
-        if (s0 + kTlTabCap >= S) break;
+        const uint32_t gbase = T * 31u * nw - 31u * hc;          // global region of local region 0
+        const uint32_t ring = (T & 1u) * nb;
+        for (uint32_t s0 = 0;; s0 += kTlTabCap) {
+          if (s0) {
+            __syncthreads();
+            if (warp == 0) build_table(T, s0);
+          }
+          __syncthreads();   // A
+          const uint32_t S = sh.n_steps;
+          const uint32_t n_round = min(S - s0, (uint32_t)kTlTabCap);
+          if (s0 == 0 && warp == NW - 1 && T + 1 < nT) {
+            // the next tile's slices into L2 while this one is processed (one request per 128 B line)
+            for (uint32_t j = lane; j < p.list_len; j += 32) {
+              const uint32_t pb = bounds[j * (nT + 1) + T + 1] & ~31u, pe = bounds[j * (nT + 1) + T + 2];
+              for (uint32_t a = pb; a < pe; a += 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(positions + a) : "memory");
+            }
+          }
+          // contiguous share of the round's steps for every warp, kTlUnroll loads in flight
+          const uint32_t per = (n_round + NW - 1) / NW;
+          const uint32_t i1 = min(warp * per + per, n_round);
+          for (uint32_t i = warp * per; i < i1; i += kTlUnroll) {
+            const uint32_t cnt = i1 - i;
+            uint32_t pv[kTlUnroll], cj[kTlUnroll];
+#pragma unroll
+            for (int u = 0; u < kTlUnroll; ++u) {
+              if (u == 0 || (uint32_t)u < cnt) {
+                const uint4 ent = tab[i + u];
+                // lanes past the end re-read the last entry (same region as their left neighbour: no
+                // mark); lane 0 without a predecessor gets a region no position can have
+                const uint32_t idx = ent.w + min(ent.x + lane, ent.y - 1u);
+                cj[u] = (lane == 0 && ent.x == kTlNone) ? ent.z ^ 0x80000000u : ent.z;
+                pv[u] = __ldg(positions + idx);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kTlUnroll; ++u) {
+              if (u == 0 || (uint32_t)u < cnt) {
+                const uint32_t l = (pv[u] - cj[u]) >> r;
+                const uint32_t lp = __shfl_up_sync(kFull, l, 1);   // lane 0 receives its own l: never a mark
+                const bool mark = l != lp;
+                const uint32_t qw = tl_div31(l), b = l - qw * 31u, bit = 1u << b;
+                const uint32_t wa = occ_s + 4u * qw;
+                const uint32_t old = tl_atoms_or(wa, bit, mark);
+                const uint32_t old2 = tl_atoms_or(wa - 4u, 0x80000000u, mark && b == 0);
+                const uint32_t self = old & (3u << b);
+                const uint32_t left = (old & (bit >> 1)) | (old2 & 0x40000000u);
+                if (__any_sync(kFull, (self | left) != 0)) {
+                  // up to two emitted regions per mark: l (a second list, or the right neighbour is
+                  // occupied) and l - 1 (the left neighbour is occupied; also the virtual region 0 of
+                  // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an
+                  // unoccupied region 0 still emits when region 1 alone reaches the threshold)
+                  const bool lo = left != 0 || (gbase + l == 1u && (old & bit) != 0);
+                  if (dense) {
+                    if (lo) tl_emit_dense(emap, l - 1u);
+                    if (self) tl_emit_dense(emap, l);
+                  } else {
+                    if (lo) {
+                      const uint32_t x = l - 1u;
+                      uint32_t slot = ring + (tl_div31(x) >> wpb_log);
+                      if (slot >= 2 * nb) slot -= 2 * nb;
+                      if (!tl_emit(bent + slot * kTlBucketCap, gbase + x)) sh.bad = 1;
+                    }
+                    if (self) {
+                      uint32_t slot = ring + (qw >> wpb_log);
+                      if (slot >= 2 * nb) slot -= 2 * nb;
+                      if (!tl_emit(bent + slot * kTlBucketCap, gbase + l)) sh.bad = 1;
+                    }
+                  }
+                }
+              }
+            }
+          }
+          if (s0 + kTlTabCap >= S) break;
+        }
+        __syncthreads();   // B
+        if (dense) {
+          // ordered scan of the tile's emit bitmap: everything below the top hc words is final
+          // (the top words travel to the next tile with the carry); the last tile scans them too
+          const uint32_t n_words = T + 1 < nT ? nw : nw + hc;
+          const uint32_t wpw = (((n_words + NW - 1) / NW) + 127u) & ~127u;   // words per warp
+          const uint32_t wb = min(warp * wpw, n_words), we = min(wb + wpw, n_words);
+          uint32_t c = 0;
+#pragma unroll 8
+          for (uint32_t w = wb + lane; w < we; w += 32) c += __popc(__ldcg(emap + w));
+          c = __reduce_add_sync(kFull, c);
+          if (lane == 0) sh.wsum[warp] = c;
+          __syncthreads();
+          uint32_t at = sh.stage_n, total = 0;
+          for (uint32_t w = 0; w < NW; ++w) {
+            const uint32_t t = sh.wsum[w];
+            if (w < warp) at += t;
+            total += t;
+          }
+          if (c) {
+            for (uint32_t w0 = wb; w0 < we; w0 += 128) {   // 4 coalesced rows of 32 words in flight
+              uint32_t bits[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t w = w0 + 32 * k + lane;
+                bits[k] = w < we ? __ldcg(emap + w) : 0u;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (!__any_sync(kFull, bits[k] != 0)) continue;
+                const uint32_t w = w0 + 32 * k + lane;
+                const uint32_t cnt = __popc(bits[k]);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                  const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                  if (lane >= o) incl += t;
+                }
+                uint32_t o = at + incl - cnt;
+                if (bits[k]) {
+                  emap[w] = 0;
+                  uint32_t bb = bits[k];
+                  while (bb) {
+                    const uint32_t b = __ffs(bb) - 1;
+                    bb &= bb - 1;
+                    if (o < out_cap) out[o] = (gbase + 31u * w + b) << r;
+                    ++o;
+                  }
+                }
+                at += __shfl_sync(kFull, incl, 31);
+              }
+            }
+          }
+          __syncthreads();
+          if (tid == 0) sh.stage_n += total;
+        }
       }
-      __syncthreads();   // B
-    }
-    if (warp == 1) finalize(nT - 1, nb + 1);
-    __syncthreads();
+      if (warp == 1 && !dense) finalize(nT - 1, nb + 1);
+      __syncthreads();
 
-    const uint32_t n = sh.stage_n;
-    if (sh.bad != 0 || n > p.staging_cap) {   // exceeds a fixed capacity: the sweep kernel redoes it
-      for (uint32_t i = tid; i < 2 * nb * kTlBucketCap; i += kThreads) bent[i] = kTlNone;
+      n = sh.stage_n;
+      if (!dense) {
+        if (sh.bad == 0 && n <= out_cap) break;
+        dense = true;     // redo: the bucket ring goes back to empty first
+        __syncthreads();
+        for (uint32_t i = tid; i < 2 * nb * kTlBucketCap; i += kThreads) bent[i] = kTlNone;
+        continue;
+      }
+      if (direct || n <= out_cap) break;
+      // more candidates than the staging area holds: the exact count is known now, write in place
       if (tid == 0) {
-        p.fallback_list[atomicAdd(p.fallback_n, 1u)] = q;
-        p.cand_off[q] = 0;
-        p.cand_cnt[q] = 0;
+        sh.base = atomicAdd(p.cand_cursor, (unsigned long long)n);
+        if (sh.base + n > p.cand_capacity) atomicExch(p.overflow, 1);
       }
       __syncthreads();
+      if (sh.base + n > p.cand_capacity) break;     // reported through p.overflow
+      out = p.cand_start + sh.base;
+      out_cap = n;
+      direct = true;
+    }
+
+    if (direct || n > out_cap) {
+      if (tid == 0) {
+        p.cand_off[q] = (uint32_t)sh.base;
+        p.cand_cnt[q] = direct && sh.base + n <= p.cand_capacity ? n : 0u;
+      }
       continue;
     }
     if (tid == 0) {

@@ -111,7 +111,7 @@ def test_config3_full_chunk():
     db = _device_chunk(ctx, seq, starts)
     queries = workloads.synth_queries(2, seq[:4 << 20].copy(), n_q, 75)
     ctx.query_upload(queries)
-    counts, ids, cand = _search_all_variants(ctx, n_q, (4, 3, 2, 1, 0))
+    counts, ids, cand = _search_all_variants(ctx, n_q, (4, 5, 6, 3, 2, 1, 0))
     assert counts.mean() > 300
     ctx.align_chunk(0)
     hits, hit_counts = ctx.results()
@@ -160,7 +160,7 @@ def test_config5_repeats_full_chunk():
     qs, _ = synth.repeat_queries(6, n_q, 75)
     queries = np.ascontiguousarray(np.stack(qs))
     ctx.query_upload(queries)
-    counts, ids, cand = _search_all_variants(ctx, n_q, (4, 3, 2, 1, 0))
+    counts, ids, cand = _search_all_variants(ctx, n_q, (4, 5, 6, 3, 2, 1, 0))
     ctx.align_chunk(0)
     hits, hit_counts = ctx.results()
     _check_properties(counts, ids, cand, hits, hit_counts, opt.best)

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 WORKLOADS = ["small", "frames6", "repeats", "long", "options"]
 
 
-@pytest.mark.parametrize("fast_search", [4, 3, 2, 1, 0])
+@pytest.mark.parametrize("fast_search", [6, 5, 4, 3, 2, 1, 0])
 @pytest.mark.parametrize("name", WORKLOADS)
 def test_stage_parity(gpu_ctx, name, fast_search):
     """(query_id, db_start) after search and (score, db_end) after SW, per candidate chunk;
