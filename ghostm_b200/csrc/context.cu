@@ -18,7 +18,7 @@ int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips);
 cudaError_t sw_extend_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream);
 cudaError_t sw_extend_s32_launch(const SwParams &p, int sm_count, cudaStream_t stream);
 uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions, bool fast);
-bool search_uses_fast(uint32_t list_len, bool allow_fast);
+bool search_uses_fast(uint32_t list_len, uint32_t threshold, bool allow_fast);
 cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream, bool allow_fast);
 bool search_bucket_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions, uint32_t *tile_bits,
                       uint32_t *bucket_cap);
@@ -44,7 +44,8 @@ bool traceback_fast_ok(uint32_t query_len, int open_gap, int extend_gap);
 bool traceback_warp_ok(uint32_t query_len, int open_gap, int extend_gap);
 cudaError_t collect_pending_launch(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
                                    uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
-                                   uint32_t *n_jobs, int sm_count, cudaStream_t stream);
+                                   uint32_t *n_jobs, uint32_t *n_left, int sm_count,
+                                   cudaStream_t stream);
 
 namespace {
 
@@ -232,6 +233,7 @@ struct gm_context {
   gm_options opt = {};
   uint32_t seed_len = 0, list_len = 0;
   bool use_s32 = false;
+  bool wide_scores = false;
   DevBuf<int32_t> matrix;
 
   DbChunk chunks[GM_MAX_DB_CHUNKS];
@@ -279,6 +281,7 @@ struct gm_context {
   bool traceback_fast = true;
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits
+  uint32_t pending_left = 0; // untraced hits the last gm_traceback_pending could not reach
   uint32_t serial = 0;
   bool imported = false;           // resident candidates came from gm_candidates_import
   uint64_t search_fallbacks = 0;   // queries redone by the sweep kernel (bucket capacities exceeded)
@@ -320,6 +323,7 @@ int derive_query_options(gm_context *c) {
     lo = std::min(lo, c->opt.score_matrix[i]);
   }
   const long max_score = (long)c->query_len * hi;
+  c->wide_scores = max_score >= 65536;   // Merge packs (score << 16 | index) records otherwise
   c->use_s32 = max_score - c->opt.open_gap > 16000 || lo - c->opt.open_gap < -16000 ||
                c->opt.open_gap < -4000 || c->opt.extend_gap < -4000 || c->opt.open_gap > 0 ||
                c->opt.extend_gap > 0;
@@ -390,9 +394,6 @@ extern "C" int gm_set_options(gm_context *c, const gm_options *opt) {
   if (int r = check_ctx(c)) return r;
   if (!opt) return fail(GM_ERR_ARGUMENT, "null options");
   if (opt->seed == 0) return fail(GM_ERR_ARGUMENT, "seed mask is 0");
-  if (opt->threshold > (uint32_t)search_max_threshold())
-    return fail(GM_ERR_UNSUPPORTED, "threshold %u > %d is not implemented by the seed-search kernel",
-                opt->threshold, search_max_threshold());
   if (opt->log_region > 20) return fail(GM_ERR_ARGUMENT, "log_region %u out of range", opt->log_region);
   c->opt = *opt;
   c->seed_len = seed_length_of(opt->seed);
@@ -424,12 +425,17 @@ extern "C" int gm_set_candidate_capacity(gm_context *c, uint64_t n) {
   return 0;
 }
 
+// Deferred TraceBack reads the residues of the hit's db chunk: hits still pending when a resident
+// chunk is replaced or released are traced first (they could never be finished afterwards).
+int trace_before_slot_change(gm_context *c, uint32_t id);
+
 extern "C" int gm_db_upload(gm_context *c, uint32_t id, const uint8_t *seq, uint32_t seq_len,
                             const uint32_t *keys_count, uint32_t keys_count_len,
                             const uint32_t *positions, uint32_t positions_len,
                             const uint32_t *seq_starts, uint32_t n_seqs) {
   if (int r = check_ctx(c)) return r;
   if (id >= GM_MAX_DB_CHUNKS) return fail(GM_ERR_ARGUMENT, "chunk id %u out of range", id);
+  if (int r = trace_before_slot_change(c, id)) return r;
   if (!seq || !keys_count || (!positions && positions_len) || !seq_starts || n_seqs == 0)
     return fail(GM_ERR_ARGUMENT, "null db arrays");
   DbChunk &ch = c->chunks[id];
@@ -463,6 +469,7 @@ extern "C" int gm_db_upload_seq(gm_context *c, uint32_t id, const uint8_t *seq, 
                                 const uint32_t *seq_starts, uint32_t n_seqs) {
   if (int r = check_ctx(c)) return r;
   if (id >= GM_MAX_DB_CHUNKS) return fail(GM_ERR_ARGUMENT, "chunk id %u out of range", id);
+  if (int r = trace_before_slot_change(c, id)) return r;
   if (!seq || !seq_starts || n_seqs == 0) return fail(GM_ERR_ARGUMENT, "null db arrays");
   DbChunk &ch = c->chunks[id];
   ch.valid = false;
@@ -490,6 +497,7 @@ extern "C" int gm_db_upload_seq(gm_context *c, uint32_t id, const uint8_t *seq, 
 extern "C" int gm_db_release(gm_context *c, uint32_t id) {
   if (int r = check_ctx(c)) return r;
   if (id >= GM_MAX_DB_CHUNKS) return fail(GM_ERR_ARGUMENT, "chunk id %u out of range", id);
+  if (int r = trace_before_slot_change(c, id)) return r;
   DbChunk &ch = c->chunks[id];
   GM_CUDA(cudaStreamSynchronize(c->stream));
   ch.seq.release(); ch.keys_count.release(); ch.positions.release(); ch.seq_starts.release();
@@ -561,11 +569,15 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
   c->cur_chunk = -1;
   c->h_counts.assign(c->n_queries, 0);
 
-  if (c->opt.threshold == 0) {
-    // aligner.cpp:416: threshold - 1 wraps to UINT_MAX, `count > threshold` is never true
+  if (c->opt.threshold == 0 || c->opt.threshold > 2 * c->list_len) {
+    // aligner.cpp:416: threshold - 1 wraps to UINT_MAX, `count > threshold` is never true; and
+    // cnt(d) + cnt(d+1) <= 2 * list_len (every list counts once per region, aligner.cpp:466-476)
     GM_CUDA(cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)c->n_queries * 4, c->stream));
     GM_CUDA(cudaMemsetAsync(c->cand_off.p, 0, (size_t)c->n_queries * 4, c->stream));
     GM_CUDA(cudaStreamSynchronize(c->stream));
+  } else if (c->opt.threshold > (uint32_t)search_max_threshold()) {
+    return fail(GM_ERR_UNSUPPORTED, "threshold %u > %d with %u lists is not implemented by the "
+                "seed-search kernel", c->opt.threshold, search_max_threshold(), c->list_len);
   } else {
     SearchParams p = {};
     p.queries = c->queries.p;
@@ -580,7 +592,7 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     p.threshold = c->opt.threshold;
     p.list_len = c->list_len;
     p.n_regions = (ch.seq_len >> c->opt.log_region) + 1;
-    const bool fast = search_uses_fast(p.list_len, c->search_fast);
+    const bool fast = search_uses_fast(p.list_len, p.threshold, c->search_fast);
     p.tile_regions = search_tile_regions((int)p.threshold, c->smem_optin, p.n_regions, fast);
     p.cand_off = c->cand_off.p;
     p.cand_cnt = c->cand_cnt.p;
@@ -1048,15 +1060,19 @@ extern "C" int gm_traceback_pending(gm_context *c, uint64_t *n_done, gm_stats *s
   if (int r = sync_chunk_tab(c)) return r;
   gm_hit *hits = c->hits[c->cur_hits].p;
   GM_CUDA(cudaMemsetAsync(c->small.p + 3, 0, 4, c->stream));
+  GM_CUDA(cudaMemsetAsync(c->small.p + 7, 0, 4, c->stream));
   GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
   GM_CUDA(collect_pending_launch(hits, c->hit_cnt[c->cur_hits].p, c->n_queries, c->cap,
-                                 c->chunk_tab.p, c->jobs.p, c->small.p + 3, c->sm_count, c->stream));
+                                 c->chunk_tab.p, c->jobs.p, c->small.p + 3, c->small.p + 7,
+                                 c->sm_count, c->stream));
   if (int r = run_traceback(c, hits)) return r;
   GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  uint32_t n = 0;
+  uint32_t n = 0, left = 0;
   GM_CUDA(cudaMemcpyAsync(&n, c->small.p + 3, 4, cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaMemcpyAsync(&left, c->small.p + 7, 4, cudaMemcpyDeviceToHost, c->stream));
   GM_CUDA(cudaStreamSynchronize(c->stream));
-  c->pending = false;
+  c->pending = left != 0;     // hits whose db chunk is not resident here stay pending
+  c->pending_left = left;
   if (n_done) *n_done = n;
   if (stats) {
     float ms = 0;
@@ -1110,6 +1126,7 @@ extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *s
   p.error = reinterpret_cast<int *>(c->small.p + 4);
   p.run_counter = c->small.p + 5;
   p.smem_elems = 1536;
+  p.wide_scores = c->wide_scores ? 1 : 0;
   p.serial = ++c->serial;
   if (p.serial == kNoId) p.serial = c->serial = 1;
   p.deferred = c->deferred ? 1 : 0;
@@ -1182,11 +1199,21 @@ extern "C" int gm_align_chunk(gm_context *c, uint32_t id, gm_stats *stats) {
   return gm_align_merge(c, stats);
 }
 
+int trace_before_slot_change(gm_context *c, uint32_t id) {
+  if (!c->pending || c->n_queries == 0 || !c->chunks[id].valid) return 0;
+  return gm_traceback_pending(c, nullptr, nullptr);
+}
+
 extern "C" int gm_results_download(gm_context *c, gm_hit *hits, uint32_t *counts) {
   if (int r = check_ctx(c)) return r;
   if (int r = ensure_query_state(c)) return r;
-  if (c->pending)
+  if (c->pending) {
     if (int r = gm_traceback_pending(c, nullptr, nullptr)) return r;
+    if (c->pending)   // never hand out half-finished records (absolute db_end, no alignment columns)
+      return fail(GM_ERR_ARGUMENT, "%u hits cannot be traced back: their db chunk is not resident in "
+                  "this context (gm_db_upload / gm_db_upload_seq it, or trace before releasing it)",
+                  c->pending_left);
+  }
   if (hits)
     GM_CUDA(cudaMemcpyAsync(hits, c->hits[c->cur_hits].p, (size_t)c->n_queries * c->cap * sizeof(gm_hit),
                             cudaMemcpyDeviceToHost, c->stream));

@@ -118,6 +118,7 @@ struct MergeParams {
   uint32_t smem_elems;         // list capacity per warp in shared memory (u32 records)
   uint32_t serial;             // id of this Merge call: marks hits accepted by it
   int deferred;                // 1: TraceBack runs later on the survivors (no job queue here)
+  int wide_scores;             // 1: a score may need more than 16 bits: 64-bit sort records only
 };
 
 // A hit whose TraceBack has not run yet carries aln_match == kNoId, aln_len == serial of the

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeParams 
       if (lane == 0) p.new_cnt[ql] = n_old;
       continue;
     }
-    if (n <= p.smem_elems && n < kCarriedFlag) {
+    if (n <= p.smem_elems && n < kCarriedFlag && !p.wide_scores) {
       merge_run<uint32_t, uint16_t>(p, my_list, my_scratch, n_new, n_old, qf, ql, lane);
     } else {
       unsigned long long base = 0;
@@ -668,14 +668,17 @@ __global__ void __launch_bounds__(256) traceback_warp_kernel(const TracebackPara
 // Collect the result slots whose TraceBack is pending and whose db chunk is resident here.
 __global__ void collect_pending_kernel(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
                                        uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
-                                       uint32_t *n_jobs) {
+                                       uint32_t *n_jobs, uint32_t *n_left) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_queries * cap;
        i += gridDim.x * blockDim.x) {
     const uint32_t q = i / cap, k = i - q * cap;
     if (k >= counts[q]) continue;
     const gm_hit &h = hits[i];
-    if (h.aln_match == kNoId && h.db_chunk < GM_MAX_DB_CHUNKS && chunks[h.db_chunk].seq != nullptr)
+    if (h.aln_match != kNoId) continue;
+    if (h.db_chunk < GM_MAX_DB_CHUNKS && chunks[h.db_chunk].seq != nullptr)
       jobs[atomicAdd(n_jobs, 1u)] = i;
+    else
+      atomicAdd(n_left, 1u);   // its db chunk is not resident here: stays pending
   }
 }
 
@@ -683,9 +686,10 @@ __global__ void collect_pending_kernel(const gm_hit *hits, const uint32_t *count
 
 cudaError_t collect_pending_launch(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
                                    uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
-                                   uint32_t *n_jobs, int sm_count, cudaStream_t stream) {
+                                   uint32_t *n_jobs, uint32_t *n_left, int sm_count,
+                                   cudaStream_t stream) {
   collect_pending_kernel<<<sm_count * 4, 256, 0, stream>>>(hits, counts, n_queries, cap, chunks, jobs,
-                                                           n_jobs);
+                                                           n_jobs, n_left);
   return cudaGetLastError();
 }
 

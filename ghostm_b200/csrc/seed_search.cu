@@ -63,20 +63,30 @@ __device__ __forceinline__ bool emits(const uint32_t *planes, uint32_t words, ui
   return r;
 }
 
+// the same for a threshold only known at run time (thresholds above 4: generic kernel, T = 0)
+__device__ __forceinline__ bool emits_rt(const uint32_t *planes, uint32_t words, uint32_t x, int T) {
+  const uint32_t w0 = x >> 5, b0 = 1u << (x & 31), w1 = (x + 1) >> 5, b1 = 1u << ((x + 1) & 31);
+  bool r = (planes[(T - 1) * words + w0] & b0) != 0;
+  for (int a = 1; a < T && !r; ++a)
+    r = (planes[(a - 1) * words + w0] & b0) && (planes[(T - a - 1) * words + w1] & b1);
+  return r;
+}
+
 template <int T>
 __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) uint32_t dyn[];
   __shared__ SearchShared sh;
+  const int TT = T ? T : (int)p.threshold;     // T == 0: threshold known at run time only (> 4)
   const uint32_t M = p.tile_regions;
   const uint32_t words = M / 32 + 1;          // +1: halo word for region base+M
   uint32_t *planes = dyn;                     // [T][words]
-  uint32_t *emitb = dyn + T * words;          // [words]
+  uint32_t *emitb = dyn + TT * words;          // [words]
   uint32_t *summary = emitb + words;          // [M/1024/32 + 1] one bit per 32-word group
   const uint32_t groups = M / 1024;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *staging = p.staging + (size_t)blockIdx.x * p.staging_cap;
 
-  for (uint32_t i = tid; i < (T + 1) * words + groups / 32 + 1; i += kSearchThreads) dyn[i] = 0;
+  for (uint32_t i = tid; i < (TT + 1) * words + groups / 32 + 1; i += kSearchThreads) dyn[i] = 0;
   if (tid == 0) sh.visited = 0;
   __syncthreads();
 
@@ -143,16 +153,16 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_kernel(const Se
                     if (pass == 1) {
                       uint32_t old = atomicOr(&planes[w], bit);
 #pragma unroll
-                      for (int t = 1; t < T; ++t)
+                      for (int t = 1; t < TT; ++t)
                         if (old & bit) old = atomicOr(&planes[t * words + w], bit); else break;
                     } else if (pass == 2) {
-                      if (in_tile && emits<T>(planes, words, x)) {
+                      if (in_tile && (T ? emits<T ? T : 1>(planes, words, x) : emits_rt(planes, words, x, TT))) {
                         atomicOr(&emitb[w], bit);
                         atomicOr(&summary[w >> 10], 1u << ((w >> 5) & 31));
                       }
                     } else {
 #pragma unroll
-                      for (int t = 0; t < T; ++t) planes[t * words + w] = 0;
+                      for (int t = 0; t < TT; ++t) planes[t * words + w] = 0;
                     }
                   }
                   const uint32_t nin = __popc(__ballot_sync(kFull, in_tile));
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_kernel(const Se
             if (pass == 1 && tile == 0 && tid == 0) {
               // aligner.cpp:451,483-494: `distance` starts at region 0 with count 0, so an
               // unoccupied region 0 still emits when region 1 alone reaches the threshold.
-              if (!(planes[0] & 1u) && (planes[(T - 1) * words] & 2u)) {
+              if (!(planes[0] & 1u) && (planes[(TT - 1) * words] & 2u)) {
                 emitb[0] |= 1u;
                 summary[0] |= 1u;
               }
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(kSearchThreads, 1) seed_search_kernel(const Se
           }
           if (tid < groups / 32 + 1) summary[tid] = 0;
           if (tid == 0) planes[words - 1] = 0;   // halo word of plane 0 .. T-1
-          if (tid < T) planes[tid * words + words - 1] = 0;
+          for (int t = tid; t < TT; t += kSearchThreads) planes[t * words + words - 1] = 0;
           __syncthreads();
         }
       }
@@ -1242,7 +1252,9 @@ int search_planes(int T, bool fast) { return (fast && T == 2) ? 1 : T; }
 
 }  // namespace
 
-bool search_uses_fast(uint32_t list_len, bool allow_fast) { return allow_fast && list_len <= kFastLists; }
+bool search_uses_fast(uint32_t list_len, uint32_t threshold, bool allow_fast) {
+  return allow_fast && list_len <= kFastLists && threshold <= 4;
+}
 
 // Largest tile (multiple of 1024 regions, at most 1024 groups) that fits `smem_limit`.
 uint32_t search_tile_regions(int T_in, size_t smem_limit, uint32_t n_regions, bool fast) {
@@ -1260,7 +1272,7 @@ uint32_t search_tile_regions(int T_in, size_t smem_limit, uint32_t n_regions, bo
 
 cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t stream, bool allow_fast) {
   const int T = (int)p.threshold;
-  const bool fast = search_uses_fast(p.list_len, allow_fast);
+  const bool fast = search_uses_fast(p.list_len, p.threshold, allow_fast);
   const size_t smem = search_smem_bytes(search_planes(T, fast), p.tile_regions);
   cudaError_t err = cudaSuccess;
 #define GM_LAUNCH_SEARCH(TT)                                                                   \
@@ -1282,7 +1294,13 @@ cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t str
     GM_LAUNCH_SEARCH(2)
     GM_LAUNCH_SEARCH(3)
     GM_LAUNCH_SEARCH(4)
-    default: return cudaErrorInvalidValue;
+    default:   // thresholds above 4: the generic kernel with run-time plane count
+      if (fast) return cudaErrorInvalidValue;
+      err = cudaFuncSetAttribute(seed_search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+      if (err != cudaSuccess) return err;
+      seed_search_kernel<0><<<grid, kSearchThreads, smem, stream>>>(p);
+      break;
   }
 #undef GM_LAUNCH_SEARCH
   return cudaGetLastError();
@@ -1360,6 +1378,6 @@ cudaError_t seed_search_hash_launch(const SearchParams &p, int sm_count, cudaStr
 }
 
 int search_max_list_len() { return kMaxListLen; }
-int search_max_threshold() { return 4; }
+int search_max_threshold() { return 1024; }   // generic kernel: one bit plane per count
 
 }  // namespace gm
