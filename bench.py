@@ -53,6 +53,10 @@ def parse_args():
     ap.add_argument("--db-residues", type=float, default=1e9)
     ap.add_argument("--chunk-mib", type=float, default=120.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 4 / config 5 blocks")
+    ap.add_argument("--extra-steps", type=int, default=2)
+    ap.add_argument("--c4-queries", type=int, default=64, help="config 4: queries per step (sample of the 10 k)")
+    ap.add_argument("--c5-queries", type=int, default=10000)
     ap.add_argument("--cpu-sample-mib", type=float, default=32.0)
     ap.add_argument("--cpu-sample-queries", type=int, default=2048)
     return ap.parse_args()
@@ -77,7 +81,7 @@ def chunk_bytes_of(a, c: int, n: int) -> int:
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index: int):
         self.proc = None
@@ -100,7 +104,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.out.close()
-        sm, mx, reasons = [], [], set()
+        sm, mx, busy, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
@@ -114,24 +118,315 @@ class ClockSampler:
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
+            try:
+                busy.append(float(f[7]))
+            except (ValueError, IndexError):
+                pass
         os.unlink(self.path)
         if not sm:
             return None
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons),
+                "gpu_busy_pct": round(statistics.mean(busy), 1) if busy else None}
 
 
 # ----------------------------------------------------------------------------- our arm
 
-class _DevArray:
-    def __init__(self, ptr: int, n: int):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False),
-                                         "version": 3, "strides": None}
+class Spec:
+    """One workload: db chunk sizes, query batches and the aligner options that differ from the
+    `ghostm aln` defaults (aligner.cpp:227-245)."""
+
+    def __init__(self, name, workload, queries, length, chunk_bytes, db_seed, q_seed, repeats=False,
+                 varlen=None, frac_db=0.5, max_list_length=1 << 27, capacity=None, n_batches=4,
+                 cpu_sample_mib=32.0, cpu_sample_queries=2048, ref_binary="ghostm"):
+        self.name, self.workload, self.queries, self.length = name, workload, queries, length
+        self.chunk_bytes, self.db_seed, self.q_seed, self.repeats = chunk_bytes, db_seed, q_seed, repeats
+        self.varlen, self.frac_db, self.max_list_length = varlen, frac_db, max_list_length
+        self.capacity = capacity or min(max(queries * 1200, 1 << 22), (1 << 32) - 1)
+        self.n_batches, self.ref_binary = n_batches, ref_binary
+        self.cpu_sample_mib, self.cpu_sample_queries = cpu_sample_mib, cpu_sample_queries
+        self.list_len = (length - 4) // 2 + 1        # (L - k) / shift + 1, aligner.cpp:399
+
+    def make_queries(self, batch, source):
+        from ghostm_b200 import workloads
+        q = workloads.synth_queries(self.q_seed + batch, source, self.queries, self.length,
+                                    frac_db=self.frac_db)
+        if self.varlen:      # `qry -l L`: shorter queries are right-padded with X = 23 (query_creator.cpp:410-412)
+            lo, hi = self.varlen
+            lens = np.random.default_rng([self.q_seed, batch, 99]).integers(lo, hi + 1, size=self.queries)
+            q[np.arange(self.length)[None, :] >= lens[:, None]] = 23
+        return q
+
+
+def _new_context(capi, local, matrix, spec):
+    ctx = capi.Context(local)
+    ctx.set_options(0xF, matrix, max_list_length=spec.max_list_length)   # -k 4, otherwise defaults
+    ctx.set_candidate_capacity(spec.capacity)
+    ctx.set_deferred_traceback(True)                  # TraceBack once, for the survivors only
+    return ctx
+
+
+class Arm:
+    """This rank's share of one workload: front context (index of the chunks c % world == rank),
+    back context (residues + .pos of every chunk; Merge + TraceBack of the rank's query slice),
+    pinned host buffers, and the pipeline (ghostm_b200.shard.GpuPipeline) - the same code path at
+    every N."""
+
+    def __init__(self, spec, torch, dist, rank, world, local, matrix, chunks=None, queries=None):
+        from ghostm_b200 import capi, shard, workloads
+        self.spec, self.torch, self.dist, self.rank, self.world, self.local = spec, torch, dist, rank, world, local
+        self.front_ctx = _new_context(capi, local, matrix, spec)
+        self.back_ctx = _new_context(capi, local, matrix, spec)
+        self.n_chunks = len(chunks) if chunks is not None else len(spec.chunk_bytes)
+        self.mine = shard.chunks_of_rank(self.n_chunks, rank, world)
+        self.sample = None
+        source = None
+        t0 = time.time()
+        for c in range(self.n_chunks):
+            if chunks is not None:
+                seq, starts = chunks[c]
+            else:
+                seq, starts = workloads.synth_chunk(spec.db_seed, c, spec.chunk_bytes[c], repeats=spec.repeats)
+            if c in self.mine:
+                self.front_ctx.db_build_index(c, seq, starts, 0xF)
+            self.back_ctx.db_upload_seq(c, seq, starts)
+            if c == 0:
+                source = seq[: 4 << 20].copy()
+                cut = max(int(np.searchsorted(starts, int(spec.cpu_sample_mib * (1 << 20)))), 2)
+                cut = min(cut, starts.shape[0] - 1)
+                self.sample = (seq[: starts[cut]].copy(), starts[:cut].copy())
+            del seq
+        if queries is not None:
+            q_all = torch.from_numpy(np.ascontiguousarray(queries))[None]
+        else:   # generated on rank 0 from db chunk 0, broadcast to every rank
+            q_all = torch.empty((spec.n_batches, spec.queries, spec.length), dtype=torch.uint8)
+            if rank == 0:
+                for b in range(spec.n_batches):
+                    q_all[b] = torch.from_numpy(spec.make_queries(b, source))
+            if world > 1:
+                qd = q_all.cuda()
+                dist.broadcast(qd, 0)
+                q_all = qd.cpu()
+        self.q_all = q_all
+        self.q_pinned = q_all.pin_memory()
+        self.cap = 10
+        self.bounds = shard.slice_bounds(None, spec.queries, world)
+        self.base, self.stop = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        n_slice = max(self.stop - self.base, 1)
+        self.hits_pinned = torch.empty((n_slice * self.cap * 9,), dtype=torch.int32).pin_memory()
+        self.counts_pinned = torch.empty((n_slice,), dtype=torch.int32).pin_memory()
+        self.stats, self.stats_back = capi.GmStats(), capi.GmStats()
+        self.pipe = shard.GpuPipeline(self.front_ctx, self.back_ctx, spec.queries, spec.length, spec.capacity,
+                                      f"cuda:{local}", dist, rank, world, self.n_chunks, self.bounds,
+                                      self.stats, self.stats_back, threaded=True)
+        self.front_stream = torch.cuda.ExternalStream(self.front_ctx.stream())
+        self.back_stream = torch.cuda.ExternalStream(self.back_ctx.stream())
+        self.setup_s = time.time() - t0
+
+    def submit(self, batch: int, e2e: bool):
+        if not e2e:
+            self.pipe.submit()
+            return
+        q = self.q_pinned[batch % self.q_pinned.shape[0]]
+        self.pipe.submit(queries_ptr=q.data_ptr(), slice_ptr=q[self.base:self.stop].data_ptr()
+                         if self.stop > self.base else 0, hits_ptr=self.hits_pinned.data_ptr(),
+                         counts_ptr=self.counts_pinned.data_ptr())
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, steps: int, warmup: int, e2e: bool):
+        """-> ([device ms, wall ms] max over ranks, [cells, candidates, launches, positions] summed over
+        ranks, rank-local stage stats, clocks (rank 0))."""
+        torch = self.torch
+        if not e2e:     # resident inputs: batch 0 uploaded once, outside the timed region
+            q = self.q_pinned[0]
+            self.front_ctx.query_upload_ptr(q.data_ptr(), self.spec.queries, self.spec.length)
+            if self.stop > self.base:
+                self.back_ctx.query_upload_ptr(q[self.base:self.stop].data_ptr(), self.stop - self.base,
+                                               self.spec.length)
+        for s in range(warmup):
+            self.submit(s, e2e)
+        self.pipe.drain()
+        self.barrier()
+        for st_ in (self.stats, self.stats_back):      # in place: the engines hold references
+            C.memset(C.byref(st_), 0, C.sizeof(st_))
+        self.pipe.front.launches = self.pipe.back.launches = 0
+        self.pipe.timers.clear()
+        sampler = ClockSampler(self.local) if self.rank == 0 else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(self.front_stream)
+        for s in range(steps):
+            self.submit(warmup + s, e2e)
+        self.pipe.drain()
+        ev1.record(self.back_stream)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if sampler else None
+        dev = f"cuda:{self.local}"
+        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+        launches = (self.stats.kernel_launches + self.stats_back.kernel_launches
+                    + self.pipe.front.launches + self.pipe.back.launches)
+        tot = torch.tensor([float(self.stats.cells), float(self.stats.candidates), float(launches),
+                            float(self.stats.seed_positions)], dtype=torch.float64, device=dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(tot, op=self.dist.ReduceOp.SUM)
+        st = self.stats.as_dict()
+        for k in ("ms_merge", "ms_traceback", "tracebacks"):
+            st[k] += getattr(self.stats_back, k)
+        st["host_ms_per_step"] = {k: round(v * 1e3 / steps, 3) for k, v in self.pipe.timers.items()}
+        return t.tolist(), tot.tolist(), st, clocks
+
+    def checksum(self, batch: int = 0):
+        """One untimed batch through the e2e path; 64-bit checksum of the downloaded hit lists, summed
+        over the ranks' slices (identical for every N: the proof that a sharded run returns the
+        single-GPU lists)."""
+        from ghostm_b200 import shard
+        self.submit(batch, True)
+        self.pipe.drain()
+        n_slice = self.stop - self.base
+        cs, rows = 0, 0
+        if n_slice:
+            hits = self.hits_pinned.numpy().view(np.uint32)[: n_slice * self.cap * 9].reshape(n_slice, self.cap, 9)
+            counts = self.counts_pinned.numpy().view(np.uint32)[:n_slice]
+            cs, rows = shard.hit_checksum(hits, counts, self.base), int(counts.sum())
+        if self.world > 1:
+            t = self.torch.tensor([cs >> 32, cs & 0xFFFFFFFF, rows], dtype=self.torch.int64, device=f"cuda:{self.local}")
+            g = [self.torch.empty_like(t) for _ in range(self.world)]
+            self.dist.all_gather(g, t)
+            cs = sum((int(x[0]) << 32) | int(x[1]) for x in g) & 0xFFFFFFFFFFFFFFFF
+            rows = sum(int(x[2]) for x in g)
+        return f"{cs:016x}", rows
+
+    def close(self):
+        self.pipe.close()
+        self.front_ctx.close()
+        self.back_ctx.close()
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _measured_traffic():
+    """dram__bytes per launch of the dominant kernels from the committed ncu summary of this round
+    (profiles/traffic.json, written from `ncu --set full` captures of this bench's launches)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+def rooflines(spec, st, n_launch_front, dpx_rate):
+    """Both roofline objects from the rank-0 stage stats of a timed region."""
+    peaks = _peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sw_s, search_s = st["ms_score"] * 1e-3, st["ms_search"] * 1e-3
+    achieved = st["cells"] * INT_OPS_PER_CELL / sw_s / 1e12 if sw_s > 0 else 0.0
+    peak = dpx_rate * DPX_OPS_PER_LANE_INSTR / 1e12
+    # SURVEY 8(d): 8 B of keys_count + 4 B of key per query k-mer, 4 B per index position, 4 B per candidate
+    search_bytes = st["seed_positions"] * 4 + spec.queries * n_launch_front * spec.list_len * 12 + st["candidates"] * 4
+    cand_per_launch = st["candidates"] / max(st["candidate_chunks"], 1)
+    traffic = _measured_traffic()
+    sw_t, se_t = traffic.get(spec.name + ":sw_extend"), traffic.get(spec.name + ":seed_search")
+    window = spec.length + 2 * 2 + 2 * 16
+    return ({"bound": "int_dpx", "kernel": "sw_extend_dpx_kernel", "achieved": achieved, "peak": peak,
+             "unit": "Tint-op/s", "frac": achieved / peak if peak else None,
+             "traffic": sw_t["dram_bytes_per_candidate"] * cand_per_launch if sw_t else None,
+             "traffic_source": sw_t["source"] if sw_t else None,
+             "algorithmic_bytes": (window + 12) * cand_per_launch,
+             "note": "achieved = SW cells x 10 int ops / SW kernel time (CUDA events on the kernel's stream, "
+                     "rank 0); peak = measured VIADDMNMX.S16x2 issue rate x 4 ops (gm_measure_dpx_peak, "
+                     "same process)",
+             "sw_gcups": st["cells"] / sw_s / 1e9 if sw_s > 0 else None},
+            {"bound": "hbm", "kernel": "seed_search_tile_kernel",
+             "achieved": search_bytes / search_s / 1e9 if search_s > 0 else None, "peak": hbm_peak,
+             "unit": "GB/s", "frac": search_bytes / search_s / 1e9 / hbm_peak if search_s > 0 else None,
+             "traffic": se_t["dram_bytes_per_position"] * st["seed_positions"] / max(n_launch_front, 1) if se_t else None,
+             "traffic_source": se_t["source"] if se_t else None,
+             "algorithmic_bytes": search_bytes / max(n_launch_front, 1),
+             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"})
+
+
+def result_block(spec, arm, steps, warmup, dpx_rate, with_clocks=True):
+    """Device-resident and e2e timing of one workload + checksum -> dict (valid on rank 0)."""
+    (dev_ms, wall_ms), (cells, cands, launches, positions), st, clocks = arm.timed(steps, warmup, False)
+    (e_dev_ms, e_wall_ms), (e_cells, _, _, _), e_st, e_clocks = arm.timed(steps, warmup, True)
+    checksum, rows = arm.checksum(0)
+    world, sharded = arm.world, arm.world > 1
+    ms_per_step = dev_ms / steps
+    roof_sw, roof_search = rooflines(spec, st, steps * len(arm.mine), dpx_rate)
+    out = {
+        "value": cells / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_per_step,
+        "queries_per_s": spec.queries / (ms_per_step * 1e-3),
+        "config": {
+            "workload": spec.workload, "queries_per_step": spec.queries, "query_len": spec.length,
+            "db_chunks": arm.n_chunks, "db_bytes": int(sum(spec.chunk_bytes)),
+            "max_list_length": spec.max_list_length,
+            "parallelism": (f"db chunks (index) sharded over {world} rank(s) for search + SW; candidates "
+                            "all-to-all by query slice over NCCL; Merge + TraceBack per query slice"
+                            if sharded else "1 rank: front context (search + SW) and back context (Merge + "
+                            "TraceBack) on one GPU, all db chunks resident"),
+            "pipeline": "back stage of batch s overlaps the front stage of batch s+1 (own stream, own host thread)",
+            "cache": "inputs larger than L2: every step streams the index positions and windows of all db "
+                     "chunks from HBM",
+            "traceback": "deferred to survivors",
+        },
+        "e2e": {"value": e_cells / (e_wall_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_wall_ms / steps,
+                "device_ms_per_step": e_dev_ms / steps,
+                "queries_per_s": spec.queries / (e_wall_ms / steps * 1e-3),
+                "h2d_bytes_per_step": int(spec.queries * spec.length) * world + int(spec.queries * spec.length),
+                "d2h_bytes_per_step": int(spec.queries * arm.cap * 36 + spec.queries * 4),
+                "gpu_busy_pct": e_clocks.get("gpu_busy_pct") if e_clocks else None},
+        "gpu_launches": int(launches),
+        "hit_list_checksum": {"value": checksum, "rows": rows,
+                              "what": "64-bit checksum of the hit lists of batch 0 downloaded through the e2e "
+                                      "path, summed over the ranks' query slices: equal at every N"},
+        "roofline": roof_sw, "roofline_seed_search": roof_search,
+        "stage_ms_per_step_rank0": {k: st[k] / steps for k in ("ms_search", "ms_score", "ms_merge", "ms_traceback")},
+        "host_ms_per_step_rank0": st.get("host_ms_per_step"),
+        "wall_ms_per_step": wall_ms / steps,
+        "e2e_host_ms_per_step_rank0": e_st.get("host_ms_per_step"),
+        "e2e_stage_ms_per_step_rank0": {k: e_st[k] / steps for k in ("ms_search", "ms_score", "ms_merge", "ms_traceback")},
+        "candidates_per_step": cands / steps, "cells_per_step": cells / steps,
+        "setup_s": arm.setup_s,
+    }
+    if with_clocks:
+        out["clocks"] = clocks
+    return out
+
+
+def specs(a):
+    n = n_db_chunks(a)
+    c3 = Spec("config3", "config3: synthetic 75-aa reads vs synthetic 1 G-residue protein db, BLOSUM62, "
+              "ghostm aln defaults", a.queries, a.length, [chunk_bytes_of(a, c, n) for c in range(n)], 1, 2,
+              cpu_sample_mib=a.cpu_sample_mib, cpu_sample_queries=a.cpu_sample_queries)
+    c4 = Spec("config4", "config4 (bounded sample of the 10 k queries): queries of U[300,1000] aa, 15 %-mutated "
+              "db substrings, X-padded to 1000 (`qry -l 1000`) vs synthetic 256 M-residue db (2 chunks); "
+              "reference semantics with the column cap raised (common.h:38 -> 1024)", a.c4_queries, 1000,
+              [128 << 20, 128 << 20], 3, 4, varlen=(300, 1000), frac_db=1.0, capacity=1 << 25, n_batches=2,
+              cpu_sample_mib=4.0, cpu_sample_queries=2, ref_binary="ghostm_l1024")
+    c5 = Spec("config5", "config5: 10 k x 75 aa queries with tandem repeats vs 64 M-residue db with 30 % "
+              "tandem repeats (period 1-4 over {A,G,S,L}), ghostm aln defaults", a.c5_queries, 75, [64 << 20], 5, 6,
+              repeats=True, capacity=1 << 29, n_batches=2, cpu_sample_mib=2.0, cpu_sample_queries=128)
+    c5l = Spec("config5_l16", c5.workload + ", -l 16 (candidate chunks of 16 Mi)", a.c5_queries, 75, [64 << 20], 5, 6,
+               repeats=True, max_list_length=16 << 20, capacity=1 << 29, n_batches=2, cpu_sample_mib=2.0,
+               cpu_sample_queries=128)
+    return c3, c4, c5, c5l
 
 
 def run_ours(a):
     import torch
-    from ghostm_b200 import capi, ring, shard, workloads
+    from ghostm_b200 import capi, workloads
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -145,230 +440,48 @@ def run_ours(a):
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    ctx = capi.Context(local)
     matrix = workloads.blosum62()
-    ctx.set_options(0xF, matrix)                      # -k 4, aligner.cpp:227-245 defaults
-    ctx.set_candidate_capacity(min(max(a.queries * 1200, 1 << 22), (1 << 32) - 1))
-    ctx.set_deferred_traceback(True)                  # TraceBack once, for the survivors only
-    sharded = world > 1
-    back_ctx = None
-    if sharded:    # Merge + TraceBack of this rank's query slice: residues + .pos of every chunk
-        back_ctx = capi.Context(local)
-        back_ctx.set_options(0xF, matrix)
-        back_ctx.set_candidate_capacity(min(max(a.queries * 1200, 1 << 22), (1 << 32) - 1))
+    c3, c4, c5, c5l = specs(a)
 
-    n_chunks = n_db_chunks(a)
-    mine = shard.chunks_of_rank(n_chunks, rank, world)
-    t_setup = time.time()
-    source = None
-    sample = None
-    for c in range(n_chunks):
-        if c not in mine and not sharded and c != 0:
-            continue
-        seq, starts = workloads.synth_chunk(1, c, chunk_bytes_of(a, c, n_chunks))
-        if c in mine:
-            ctx.db_build_index(c, seq, starts, 0xF)
-        if sharded:
-            back_ctx.db_upload_seq(c, seq, starts)
-        if c == 0:
-            source = seq[: 4 << 20].copy()
-            cut = int(np.searchsorted(starts, int(a.cpu_sample_mib * (1 << 20))))
-            cut = max(cut, 2)
-            sample = (seq[: starts[cut]].copy(), starts[:cut].copy())
-        del seq
-    # query batches: generated on rank 0 from db chunk 0, broadcast to every rank
-    n_batches = 4
-    q_all = torch.empty((n_batches, a.queries, a.length), dtype=torch.uint8)
-    if rank == 0:
-        for b in range(n_batches):
-            q_all[b] = torch.from_numpy(workloads.synth_queries(2 + b, source, a.queries, a.length))
-    if world > 1:
-        qd = q_all.cuda()
-        dist.broadcast(qd, 0)
-        q_all = qd.cpu()
-    q_pinned = q_all.pin_memory()
-    cap = 10
-    bounds = shard.slice_bounds(None, a.queries, world)
-    base, stop = int(bounds[rank]), int(bounds[rank + 1])
-    hits_pinned = torch.empty(((stop - base) * cap * 9,), dtype=torch.int32).pin_memory()
-    counts_pinned = torch.empty((stop - base,), dtype=torch.int32).pin_memory()
-    setup_s = time.time() - t_setup
-
-    dpx_rate = ctx.measure_dpx_peak()
-    stats = capi.GmStats()
-    stats_back = capi.GmStats()
-    front = back = None
-    if sharded:
-        front = shard.GpuFront(ctx, a.queries, min(max(a.queries * 1200, 1 << 22), (1 << 32) - 1),
-                               f"cuda:{local}", stats)
-        back = shard.GpuBack(back_ctx, stats_back)
-
-    class GpuEngine(ring.Engine):
-        def prepare(self, c):
-            ctx.align_prepare(c, stats)
-
-        def merge(self):
-            ctx.align_merge(stats)
-
-        def list_tensors(self):
-            hp, cp = ctx.results_device()
-            dev = f"cuda:{local}"
-            return (torch.as_tensor(_DevArray(hp, a.queries * cap * 9), device=dev),
-                    torch.as_tensor(_DevArray(cp, a.queries), device=dev))
-
-        def lists_received(self):
-            torch.cuda.synchronize()
-
-    engine = GpuEngine()
-    stream = torch.cuda.ExternalStream(ctx.stream())
-    stream_end = torch.cuda.ExternalStream(back_ctx.stream()) if sharded else stream
-
-    host_t = {}
-
-    def step(s: int, e2e: bool):
-        b = s % n_batches
-        t_0 = time.perf_counter()
-        if not sharded:
-            if e2e:
-                ctx.query_upload_ptr(q_pinned[b].data_ptr(), a.queries, a.length)
-            else:
-                ctx.results_clear()
-            ring.ring_step(engine, dist, rank, world, n_chunks)
-            ctx.traceback_pending(stats)
-            if e2e:
-                ctx.results_download_ptr(hits_pinned.data_ptr(), counts_pinned.data_ptr())
-            return
-        if e2e:   # every rank needs all queries (front) and its own slice again (back)
-            ctx.query_upload_ptr(q_pinned[b].data_ptr(), a.queries, a.length)
-            back_ctx.query_upload_ptr(q_pinned[b][base:stop].data_ptr(), stop - base, a.length)
-        else:
-            back_ctx.results_clear()
-        host_t["upload"] = host_t.get("upload", 0.0) + time.perf_counter() - t_0
-        shard.shard_step(front, back, dist, rank, world, n_chunks, bounds,
-                         before_back=torch.cuda.synchronize, timers=host_t)
-        t_1 = time.perf_counter()
-        if e2e:
-            back_ctx.results_download_ptr(hits_pinned.data_ptr(), counts_pinned.data_ptr())
-        host_t["download"] = host_t.get("download", 0.0) + time.perf_counter() - t_1
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(e2e: bool):
-        if not e2e:
-            ctx.query_upload_ptr(q_pinned[0].data_ptr(), a.queries, a.length)
-            if sharded:
-                back_ctx.query_upload_ptr(q_pinned[0][base:stop].data_ptr(), stop - base, a.length)
-        for s in range(a.warmup):
-            step(s, e2e)
-        barrier()
-        for st_ in (stats, stats_back):      # in place: the engines hold references
-            C.memset(C.byref(st_), 0, C.sizeof(st_))
-        if sharded:
-            front.launches = back.launches = 0
-        host_t.clear()
-        sampler = ClockSampler(local) if rank == 0 else None
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev0.record(stream)
-        for s in range(a.steps):
-            step(a.warmup + s, e2e)
-        ev1.record(stream_end)
-        barrier()
-        wall = time.perf_counter() - t0
-        dev_ms = ev0.elapsed_time(ev1)
-        clocks = sampler.stop() if sampler else None
-        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=f"cuda:{local}")
-        launches = stats.kernel_launches + stats_back.kernel_launches
-        if sharded:
-            launches += front.launches + back.launches
-        cells = torch.tensor([float(stats.cells), float(stats.candidates), float(launches),
-                              float(stats.seed_positions)], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(cells, op=dist.ReduceOp.SUM)
-        st = stats.as_dict()
-        for k in ("ms_merge", "ms_traceback", "tracebacks", "candidate_chunks"):
-            st[k] += getattr(stats_back, k)
-        st["host_ms_per_step"] = {k: round(v * 1e3 / a.steps, 3) for k, v in host_t.items()}
-        return t.tolist(), cells.tolist(), st, clocks
-
-    (dev_ms, wall_ms), (cells, cands, launches, positions), st, clocks = timed(False)
-    (e_dev_ms, e_wall_ms), (e_cells, _, _, _), e_st, _ = timed(True)
-
+    arm = Arm(c3, torch, dist, rank, world, local, matrix)
+    dpx_rate = arm.front_ctx.measure_dpx_peak()
+    block = result_block(c3, arm, a.steps, a.warmup, dpx_rate)
     out = None
     if rank == 0:
-        ms_per_step = dev_ms / a.steps
-        value = cells / (dev_ms * 1e-3) / 1e9
-        e2e_value = e_cells / (e_wall_ms * 1e-3) / 1e9
-        sw_s = st["ms_score"] * 1e-3
-        achieved = st["cells"] * INT_OPS_PER_CELL / sw_s / 1e12 if sw_s > 0 else 0.0
-        peak = dpx_rate * DPX_OPS_PER_LANE_INSTR / 1e12
-        search_s = st["ms_search"] * 1e-3
-        search_bytes = (st["seed_positions"] * 4 + a.queries * a.steps * len(mine) * 36 * 12
-                        + st["candidates"] * 4)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "s16", "data": "synthetic",
-            "queries_per_s": a.queries / (ms_per_step * 1e-3),
-            "config": {
-                "workload": "config3: synthetic 75-aa reads vs synthetic 1 G-residue protein db, "
-                            "BLOSUM62, ghostm aln defaults",
-                "queries_per_step": a.queries, "query_len": a.length,
-                "db_residues": a.db_residues, "db_chunks": n_chunks, "chunk_mib": a.chunk_mib,
-                "parallelism": (f"db chunks (index) sharded over {world} rank(s) for search + SW; "
-                                "candidates all-to-all by query slice over NCCL; Merge + TraceBack "
-                                "per query slice" if sharded else "1 rank, all db chunks resident"),
-                "cache": "inputs larger than L2: every step streams the index positions and "
-                         "windows of all db chunks (>=0.6 GB per chunk) from HBM",
-                "traceback": "deferred to survivors",
-            },
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e_wall_ms / a.steps,
-                    "queries_per_s": a.queries / (e_wall_ms / a.steps * 1e-3),
-                    "h2d_bytes_per_step": int(a.queries * a.length) * (world + (1 if sharded else 0)),
-                    "d2h_bytes_per_step": int(a.queries * cap * 36 + a.queries * 4)},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "int_dpx", "kernel": "sw_extend_dpx_kernel<75>",
-                         "achieved": achieved, "peak": peak, "unit": "Tint-op/s",
-                         "frac": achieved / peak if peak else None,
-                         # dram__bytes_read+write of one `ncu --set full` capture of this kernel
-                         # (profiles/r1_sw_extend_ncu.md: 611.0 MB for 5,595,674 candidates),
-                         # scaled to the candidates of one launch of this run
-                         "traffic": 611.0e6 / 5595674 * (st["candidates"] / max(a.steps * len(mine), 1)),
-                         "algorithmic_bytes": (a.length + 36 + 12) * (st["candidates"] / max(a.steps * len(mine), 1)),
-                         "note": "achieved = SW cells x 10 int ops / SW kernel time (CUDA events, "
-                                 "rank 0); peak = measured VIADDMNMX.S16x2 issue rate x 4 ops "
-                                 "(gm_measure_dpx_peak, same process)",
-                         "sw_gcups": st["cells"] / sw_s / 1e9 if sw_s > 0 else None},
-            "roofline_seed_search": {"bound": "hbm", "achieved": search_bytes / search_s / 1e9
-                                     if search_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": search_bytes / search_s / 1e9 / hbm_peak
-                                     if search_s > 0 else None,
-                                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-            "stage_ms_per_step_rank0": {k: st[k] / a.steps for k in
-                                        ("ms_search", "ms_score", "ms_merge", "ms_traceback")},
-            "host_ms_per_step_rank0": st.get("host_ms_per_step"),
-            "wall_ms_per_step": wall_ms / a.steps,
-            "e2e_host_ms_per_step_rank0": e_st.get("host_ms_per_step"),
-            "setup_s": setup_s,
-        }
+        out = {"metric": METRIC, "value": block.pop("value"), "unit": block.pop("unit"), "n_gpus": world,
+               "steps": a.steps, "warmup": a.warmup, "ms_per_step": block.pop("ms_per_step"),
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s16",
+               "data": "synthetic"}
+        out.update(block)
         if world == 1 and not a.no_cpu_baseline:
             try:
-                out["cpu_baseline"] = cpu_baseline(a, ctx, sample, q_all[0].numpy(), matrix)
+                out["cpu_baseline"] = cpu_baseline(c3, arm.sample, arm.q_all[0].numpy(), matrix, torch, local)
             except Exception as e:  # the baseline is reported, never allowed to hide the GPU number
                 out["cpu_baseline"] = {"error": repr(e)}
+    arm.close()
+    del arm
+
+    extra = {}
+    if not a.no_extra:
+        for spec in (c4, c5, c5l):
+            try:
+                arm = Arm(spec, torch, dist, rank, world, local, matrix)
+                blk = result_block(spec, arm, a.extra_steps, 1, dpx_rate, with_clocks=False)
+                blk["steps"], blk["warmup"] = a.extra_steps, 1
+                if rank == 0 and world == 1 and not a.no_cpu_baseline and spec is not c5l:
+                    try:
+                        blk["cpu_baseline"] = cpu_baseline(spec, arm.sample, arm.q_all[0].numpy(), matrix, torch, local)
+                    except Exception as e:
+                        blk["cpu_baseline"] = {"error": repr(e)}
+                arm.close()
+                del arm
+                extra[spec.name] = blk
+            except Exception as e:
+                if world > 1:
+                    raise          # a rank that skips a collective would hang the others
+                extra[spec.name] = {"error": repr(e)}
+    if out is not None:
+        out["extra"] = extra
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -397,50 +510,55 @@ def _write_sample(tmp, seq, starts, queries, n_qchunks):
     return db, qcs
 
 
-def _ref_binary():
-    p = os.path.join(ROOT, "oracle", "_ref", "ghostm")
+def _ref_binary(name="ghostm"):
+    p = os.path.join(ROOT, "oracle", "_ref", name)
     return p if os.path.exists(p) else None
 
 
-def cpu_baseline(a, ctx, sample, queries, matrix):
-    """The reference CPU aligner (oracle/_ref/ghostm, else the oracle port) on a bounded sample of
-    the same workload, one host thread, with a parity check of its output against the GPU path."""
-    from ghostm_b200 import capi
+def cpu_baseline(spec, sample, queries, matrix, torch, local):
+    """The reference CPU aligner (oracle/_ref/<binary>, else the oracle port) on a bounded sample of
+    the same workload, one host thread, with a byte comparison of its output against the GPU path
+    (the same front / back pipeline as the timed run)."""
     from oracle import oracle as O
     seq, starts = sample
-    qs = np.ascontiguousarray(queries[: a.cpu_sample_queries])
+    qs = np.ascontiguousarray(queries[: spec.cpu_sample_queries])
     tmp = tempfile.mkdtemp(prefix="gm_cpu_")
     try:
         db, qcs = _write_sample(tmp, seq, starts, qs, 1)
         # GPU on the sample: cells and hit lists
-        g = capi.Context(int(os.environ.get("LOCAL_RANK", 0)))
-        g.set_options(0xF, matrix)
-        g.db_upload(0, db.chunks[0])
-        g.query_upload(qs)
-        st = capi.GmStats()
-        g.align_chunk(0, st)
-        hits, counts = g.results()
-        g.close()
+        sub = Spec(spec.name + "_sample", "", qs.shape[0], spec.length, [seq.shape[0]], 0, 0,
+                   max_list_length=spec.max_list_length, capacity=1 << 26)
+        arm = Arm(sub, torch, None, 0, 1, local, matrix, chunks=[(seq, starts)], queries=qs)
+        arm.submit(0, True)
+        arm.pipe.drain()
+        cells = int(arm.stats.cells)
+        hits = arm.hits_pinned.numpy().view(np.uint32).reshape(qs.shape[0], arm.cap, 9).copy()
+        counts = arm.counts_pinned.numpy().view(np.uint32).copy()
+        arm.close()
+        opt = O.Options(max_list_length=spec.max_list_length)
         res = O.ResultLists(qs.shape[0], 10)
-        res.hits[:] = hits
+        res.hits[:] = hits.view(res.hits.dtype).reshape(res.hits.shape)
         res.counts[:] = counts
-        gpu_text = O.format_output(res, qcs[0], db, O.Options())
-        ref = _ref_binary()
+        gpu_text = O.format_output(res, qcs[0], db, opt)
+        ref = _ref_binary(spec.ref_binary)
         t0 = time.perf_counter()
         if ref:
-            subprocess.check_call([ref, "aln", "-i", os.path.join(tmp, "q"), "-d",
-                                   os.path.join(tmp, "db"), "-o", os.path.join(tmp, "out.txt")],
-                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            cmd = [ref, "aln", "-i", os.path.join(tmp, "q"), "-d", os.path.join(tmp, "db"), "-o",
+                   os.path.join(tmp, "out.txt")]
+            if spec.max_list_length != 1 << 27:
+                cmd += ["-l", str(spec.max_list_length >> 20)]
+            subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
             wall = time.perf_counter() - t0
             cpu_text = open(os.path.join(tmp, "out.txt"), encoding="latin-1").read()
             kind = "reference"
         else:
-            r = O.align_chunk(qcs[0], db, O.Options())
+            r = O.align_chunk(qcs[0], db, opt)
             wall = time.perf_counter() - t0
-            cpu_text = O.format_output(r, qcs[0], db, O.Options())
+            cpu_text = O.format_output(r, qcs[0], db, opt)
             kind = "port"
-        return {"value": st.cells / wall / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
-                "sample": f"{qs.shape[0]} queries x {a.length} aa vs the first "
+        return {"value": cells / wall / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+                "binary": spec.ref_binary if ref else None,
+                "sample": f"{qs.shape[0]} queries x {spec.length} aa vs the first "
                           f"{seq.shape[0] / (1 << 20):.1f} MiB of db chunk 0, whole `ghostm aln` run "
                           f"(search+SW+merge+traceback+output), {wall:.1f} s",
                 "queries_per_s": qs.shape[0] / wall,

@@ -345,6 +345,9 @@ __device__ __forceinline__ bool arrive_decide(uint32_t *p0, uint32_t *emitb, uin
                                               uint32_t x, bool halo) {
   const uint32_t w = x >> 5, b = x & 31, bit = 1u << b;
   const uint32_t old = atomicOr(&p0[w], bit);
+  // two marks in adjacent regions that straddle a word boundary each set their own word and then
+  // read the other's: without a fence between the two accesses both could miss each other
+  if (b == 0 || b == 31) __threadfence_block();
   bool self = false, left = false;
   if (!halo) {
     self = (old & bit) != 0;

@@ -1,4 +1,5 @@
-"""CPU: formats, the C ABI surface, the chunk rule, the introsort restatement, the gloo ring."""
+"""CPU: formats, the C ABI surface, the chunk rule, the introsort restatement, the sharded driver
+over gloo."""
 import ctypes
 import os
 import re
@@ -8,7 +9,7 @@ import sys
 import numpy as np
 import pytest
 
-from ghostm_b200 import capi, formats, ring, synth
+from ghostm_b200 import capi, formats, shard, synth
 from oracle import oracle as O
 from tests import helpers as H
 
@@ -131,70 +132,12 @@ def test_writers_byte_identical_to_reference(tmp_path):
 def test_chunks_of_rank_partition():
     for n in (1, 3, 8, 9):
         for w in (1, 2, 4, 8):
-            parts = [ring.chunks_of_rank(n, r, w) for r in range(w)]
+            parts = [shard.chunks_of_rank(n, r, w) for r in range(w)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert all(c % w == r for r, p in enumerate(parts) for c in p)
 
 
-_RING_WORKER = r"""
-import os, sys
-sys.path.insert(0, {root!r})
-import numpy as np, torch, torch.distributed as dist
-from ghostm_b200 import ring
-from oracle import oracle as O
-from tests import helpers as H
-
-rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-dist.init_process_group("gloo")
-db, qchunks, kw = H.workload("small")
-opt = O.Options(**kw)
-qc = qchunks[0]
-
-class OracleEngine(ring.Engine):
-    def __init__(self):
-        self.res = O.ResultLists(qc.n, opt.best)
-        self.t_hits = torch.from_numpy(self.res.hits.view(np.int32).reshape(-1))
-        self.t_counts = torch.from_numpy(self.res.counts.view(np.int32))
-        self.stage = None
-    def prepare(self, c):
-        ch = db.chunks[c]
-        self.stage = (c, [(ids, st) + O.calculate_score(qc.seqs, ch, ids, st, opt)
-                          for ids, st in O.search_chunks(qc.seqs, ch, opt)])
-    def merge(self):
-        c, parts = self.stage
-        for ids, st, sc, en in parts:
-            O.merge(self.res, qc, db.chunks[c], c, ids, st, sc, en, opt)
-    def list_tensors(self):
-        return self.t_hits, self.t_counts
-
-eng = OracleEngine()
-final = ring.ring_step(eng, dist, rank, world, len(db.chunks))
-if final:
-    single = O.align_chunk(qc, db, opt)
-    assert np.array_equal(single.counts, eng.res.counts)
-    for i in range(qc.n):
-        assert single.hits[i, :single.counts[i]].tobytes() == eng.res.hits[i, :single.counts[i]].tobytes()
-    print("RING_OK", int(single.counts.sum()))
-dist.barrier()
-dist.destroy_process_group()
-"""
-
-
-def test_ring_over_gloo_world2(tmp_path):
-    """db chunks sharded over 2 ranks, hit lists handed rank 0 -> rank 1 (gloo): the last rank must
-    hold exactly the single-process result."""
-    script = tmp_path / "w.py"
-    script.write_text(_RING_WORKER.format(root=ROOT))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
-                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29611",
-                          str(script)], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr[-2000:]
-    assert "RING_OK" in out.stdout
-
-
 # ---- ghostm_b200.shard: chunk-parallel front, query-sliced back ------------------------------
-
-from ghostm_b200 import shard
 
 
 def test_slice_bounds_respect_runs():
@@ -256,14 +199,25 @@ from tests.test_host_logic import _assert_slices_equal_single
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
-db, qchunks, kw = H.workload("small")
+db, qchunks, kw = H.workload({workload!r})
+kw.update({extra!r})
 opt = O.Options(**kw)
 qc = qchunks[0]
 bounds = shard.slice_bounds(qc.name_breaks(), qc.n, world)
 front = H.OracleFront(qc, db, opt)
 back = H.OracleBack(H.slice_query_chunk(qc, int(bounds[rank]), int(bounds[rank + 1])), db, opt)
-shard.shard_step(front, back, dist, rank, world, len(db.chunks), bounds)
-backs = [back if r == rank else None for r in range(world)]
+worker = shard.BackWorker() if {threaded!r} else None
+done = []
+for batch in range(2):      # two batches: the second front overlaps the first back on the worker
+    if batch:
+        if worker: worker.drain()
+        back.reset()
+    shard.shard_step(front, back, dist, rank, world, len(db.chunks), bounds, worker=worker,
+                     after_back=lambda: done.append(1))
+if worker:
+    worker.drain()
+    worker.close()
+assert len(done) == 2
 single = O.align_chunk(qc, db, opt)
 base, stop = int(bounds[rank]), int(bounds[rank + 1])
 assert np.array_equal(single.counts[base:stop], back.res.counts)
@@ -278,11 +232,15 @@ dist.destroy_process_group()
 """
 
 
-def test_shard_over_gloo_world2(tmp_path):
+@pytest.mark.parametrize("workload,extra,threaded", [("small", {}, False), ("small", {}, True),
+                                                     ("repeats", {"max_list_length": 8}, True)])
+def test_shard_over_gloo_world2(tmp_path, workload, extra, threaded):
     """db chunks sharded over 2 ranks, candidates exchanged by query slice over gloo all-to-all:
-    each rank must hold exactly the single-process lists of its slice."""
+    each rank must hold exactly the single-process lists of its slice - inline and with the back
+    stage on its worker thread, and with more candidate chunks per db chunk (-l 8) than the first
+    meta exchange carries."""
     script = tmp_path / "w.py"
-    script.write_text(_SHARD_WORKER.format(root=ROOT))
+    script.write_text(_SHARD_WORKER.format(root=ROOT, workload=workload, extra=extra, threaded=threaded))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                           "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29613",
                           str(script)], capture_output=True, text=True, timeout=600)
