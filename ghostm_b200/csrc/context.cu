@@ -27,8 +27,9 @@ bool search_hash_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions);
 cudaError_t seed_search_hash_launch(const SearchParams &p, int sm_count, cudaStream_t stream);
 cudaError_t seed_search_bucket_launch(const SearchParams &p, int sm_count, cudaStream_t stream);
 bool search_tile_geometry(uint32_t threshold, uint32_t list_len, uint32_t shift, uint32_t log_region,
-                          uint32_t seq_len, uint32_t n_keys, TileGeometry *g);
+                          uint32_t seq_len, uint32_t n_keys, size_t smem_per_sm, TileGeometry *g);
 int search_tile_grid(int sm_count);
+size_t search_tile_emap_words(const TileGeometry &g);
 cudaError_t search_split_build(const uint32_t *keys_count, uint32_t n_keys, const uint32_t *positions,
                                const TileGeometry &g, uint32_t *split, int sm_count, cudaStream_t stream);
 cudaError_t seed_search_tile_launch(SearchParams p, const TileGeometry &g, int sm_count,
@@ -226,6 +227,7 @@ struct gm_context {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
+  size_t smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {};
 
@@ -360,6 +362,7 @@ extern "C" int gm_create(int device, gm_context **out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
+  c->smem_per_sm = prop.sharedMemPerMultiprocessor;
   GM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto &e : c->ev) GM_CUDA(cudaEventCreate(&e));
   GM_CUDA(c->counters.ensure(8));
@@ -608,7 +611,7 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     TileGeometry tg = {};
     const bool tile = c->search_tile && c->search_fast && ch.keys_count_len > 1 &&
                       search_tile_geometry(p.threshold, p.list_len, p.shift, p.log_region, ch.seq_len,
-                                           ch.keys_count_len - 1, &tg);
+                                           ch.keys_count_len - 1, c->smem_per_sm, &tg);
     if (tile) {
       if (!ch.split_valid || memcmp(&ch.split_geom, &tg, sizeof(tg)) != 0) {
         ch.split_valid = false;
@@ -620,15 +623,16 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
       }
       GM_CUDA(c->staging.ensure((size_t)search_tile_grid(c->sm_count) * c->staging_cap));
       p.staging = c->staging.p;
-      // dense-mode emit bitmaps, one per CTA; the kernel leaves them all zero
-      const size_t emap_words = (size_t)search_tile_grid(c->sm_count) * ((tg.nw + tg.hc + 3u) & ~3u);
+      // emit bitmaps (absolute region words of the chunk), one per CTA; the kernel leaves them all zero
+      const size_t emap_stride = search_tile_emap_words(tg);
+      const size_t emap_words = (size_t)search_tile_grid(c->sm_count) * emap_stride;
       if (c->tile_emap.n < emap_words) {
         GM_CUDA(c->tile_emap.ensure(emap_words));
-        GM_CUDA(cudaMemsetAsync(c->tile_emap.p, 0, emap_words * 4, c->stream));
+        GM_CUDA(cudaMemsetAsync(c->tile_emap.p, 0, c->tile_emap.n * 4, c->stream));
       }
       p.split = ch.split.p;
       p.tl_emap = c->tile_emap.p;
-      p.tl_force_dense = c->tile_test >= 1;
+      p.tl_emap_stride = emap_stride;
       if (c->tile_test >= 2) p.staging_cap = 16;
     }
     const bool hash = !tile && c->search_hash && c->search_fast &&
@@ -654,7 +658,7 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
       p.fallback_n = c->small.p + 6;
     }
     GM_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    if (tile) {   // no capacity anywhere (sparse, dense and in-place attempts inside the kernel)
+    if (tile) {   // no capacity anywhere: staged, else counted and written in place
       GM_CUDA(seed_search_tile_launch(p, tg, c->sm_count, c->stream));
     } else if (bucket || hash) {
       if (hash) GM_CUDA(seed_search_hash_launch(p, c->sm_count, c->stream));

@@ -72,16 +72,17 @@ struct SearchParams {
   // tile kernel (threshold 2, seed_search_tile.cu)
   const uint32_t *split;       // [n_keys * tl_tiles + 1] per-key tile boundaries inside positions[]
   uint32_t tl_nw, tl_hc;       // bitmap words per tile (31 regions each) + carried halo words
-  uint32_t tl_nb, tl_wpb_log;  // range buckets per tile, log2 words per bucket (tl_nw = tl_nb << tl_wpb_log)
   uint32_t tl_tiles;
-  uint32_t tl_force_dense;     // tests: skip the sparse attempt
-  uint32_t *tl_emap;           // [gridDim.x][tl_nw + tl_hc rounded up to 4] dense-mode emit bitmaps, all zero
+  uint32_t tl_ring;            // words of the shared-memory summary ring (power of two)
+  uint32_t *tl_emap;           // [gridDim.x][tl_emap_stride] emit bitmaps (absolute region words), all zero
+  size_t tl_emap_stride;
 };
 
 // Geometry of the tiled seed search for one db chunk (search_tile_geometry).
 struct TileGeometry {
-  uint32_t nw, hc, nb, wpb_log, n_tiles;
+  uint32_t nw, hc, n_tiles;
   uint32_t tile_pos;           // positions per tile: (31 * nw) << log_region
+  uint32_t ring;               // summary ring words
 };
 
 // ---- merge / traceback --------------------------------------------------------------

@@ -1,12 +1,11 @@
-"""Tile seed-search kernel: tuning sweep (GM_TILE_CFG = warps,buckets,log2 words per bucket,CTAs/SM)
+"""Tile seed-search kernel: tuning sweep (GM_TILE_CFG = warps per CTA,CTAs per SM)
 on one config-3 chunk, every setting compared candidate for candidate with the bucket kernel."""
 import os, sys, json
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ghostm_b200 import capi, workloads
 n_q = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-cfgs = sys.argv[2:] or ["12,48,8,3", "8,32,8,4", "8,32,8,5", "16,64,8,2", "12,64,8,2", "6,24,8,6", "4,16,8,8",
-                        "8,48,8,3", "12,32,8,3"]
+cfgs = sys.argv[2:] or ["16,2", "12,2", "20,2", "10,3", "8,4", "24,1", "32,1"]
 ctx = capi.Context(0)
 ctx.set_options(0xF, workloads.blosum62())
 ctx.set_candidate_capacity(1 << 26)
