@@ -28,7 +28,7 @@ EXTENDED_SYMBOLS = ["gm_version", "gm_last_error", "gm_device_count", "gm_create
                     "gm_results_device", "gm_stream", "gm_measure_dpx_peak",
                     "gm_set_deferred_traceback", "gm_traceback_pending", "gm_set_search_variant",
                     "gm_align_prepare", "gm_align_merge", "gm_db_upload_seq", "gm_candidates_pack",
-                    "gm_candidates_import", "gm_candidates_transfer"]
+                    "gm_candidates_import", "gm_candidates_transfer", "gm_device_memory"]
 
 HIT_DTYPE = np.dtype([("query_id", "<u4"), ("db_id", "<u4"), ("db_chunk", "<u4"), ("score", "<u4"),
                       ("db_start", "<u4"), ("db_end", "<u4"), ("aln_len", "<u4"),

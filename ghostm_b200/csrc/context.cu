@@ -374,6 +374,15 @@ extern "C" int gm_create(int device, gm_context **out) {
   return 0;
 }
 
+extern "C" int gm_device_memory(gm_context *c, uint64_t *free_bytes, uint64_t *total_bytes) {
+  if (int r = check_ctx(c)) return r;
+  size_t f = 0, t = 0;
+  GM_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return 0;
+}
+
 extern "C" void gm_destroy(gm_context *c) {
   if (!c) return;
   cudaSetDevice(c->device);

@@ -260,8 +260,25 @@ Options parse_options(int argc, char **argv) {
   return o;
 }
 
+struct DeviceError : std::runtime_error {   // a gm_* call failed: non-zero exit status, no partial output file
+  explicit DeviceError(const std::string &m) : std::runtime_error(m) {}
+};
+
 void check(int rc, const char *what) {
-  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + gm_last_error());
+  if (rc != 0) throw DeviceError(std::string(what) + ": " + gm_last_error());
+}
+
+// gm_align_chunk / gm_search stop with GM_ERR_CAPACITY before anything was merged when skewed data
+// produces more candidates than the buffer holds: double the buffer and redo the call.
+template <typename F>
+void with_capacity_retry(gm_context *ctx, uint64_t *capacity, const char *what, F call) {
+  int rc = call();
+  while (rc == GM_ERR_CAPACITY && *capacity < 0xFFFFFFFFull) {
+    *capacity = std::min<uint64_t>(*capacity * 2, 0xFFFFFFFFull);
+    check(gm_set_candidate_capacity(ctx, *capacity), "gm_set_candidate_capacity");
+    rc = call();
+  }
+  check(rc, what);
 }
 
 // ---- several devices: chunk-parallel front, query-sliced back ------------
@@ -280,10 +297,12 @@ std::vector<uint32_t> slice_bounds(const std::vector<uint8_t> &name_break, uint3
 }
 
 // Seed search + SW extension of one db chunk for all queries; the candidate-chunk segments.
-std::vector<Segment> front_chunk(gm_context *ctx, uint32_t chunk, uint32_t n_queries, uint32_t max_list_length) {
+std::vector<Segment> front_chunk(gm_context *ctx, uint32_t chunk, uint32_t n_queries, uint32_t max_list_length,
+                                 uint64_t *capacity, gm_stats *stats) {
   std::vector<uint32_t> counts(n_queries);
   uint64_t total = 0;
-  check(gm_search(ctx, chunk, counts.data(), &total, nullptr), "gm_search");
+  with_capacity_retry(ctx, capacity, "gm_search",
+                      [&] { return gm_search(ctx, chunk, counts.data(), &total, stats); });
   std::vector<Segment> segs;
   uint32_t first = 0;
   while (true) {
@@ -291,7 +310,7 @@ std::vector<Segment> front_chunk(gm_context *ctx, uint32_t chunk, uint32_t n_que
     int last = 0;
     const uint32_t end = gm_chunk_rule(counts.data(), n_queries, first, max_list_length, &n, &last);
     if (n == 0) break;                                   // aligner.cpp:136-139
-    check(gm_score(ctx, first, end, nullptr, nullptr, nullptr), "gm_score");
+    check(gm_score(ctx, first, end, nullptr, nullptr, stats), "gm_score");
     segs.push_back(Segment{first, end});
     if (last) break;
     first = end;
@@ -301,6 +320,8 @@ std::vector<Segment> front_chunk(gm_context *ctx, uint32_t chunk, uint32_t n_que
 
 struct Shard {            // one device of a multi-device run
   gm_context *front = nullptr, *back = nullptr;
+  uint64_t capacity = 0;
+  gm_stats stats;
   std::mutex front_mu;    // gm_candidates_transfer is serialised per sending context
   std::vector<Segment> segs;
   std::string error;
@@ -349,8 +370,11 @@ void write_hits(std::ostream &out, const Options &o, const QueryChunk &q, const 
   }
 }
 
+std::string g_output_path;   // removed when the run dies on a device error
+
 int run_aln(int argc, char **argv) {
   Options o = parse_options(argc, argv);
+  g_output_path = o.output;
   const ScoreMatrix sm = load_matrix(o.matrix_file);
   Karlin karlin = {0, 0, 0};
   if (o.style == 0) karlin = gapped_karlin(sm, o.open_gap, o.extend_gap);
@@ -389,9 +413,18 @@ int run_aln(int argc, char **argv) {
       check(gm_set_options(shards[d].back, &go), "gm_set_options");
     }
   }
-  // db chunks: resident for the whole run (the reference re-reads them per query chunk)
+  // db chunks: resident in HBM for the whole run while they fit (the reference re-reads and
+  // re-uploads every chunk for every query chunk, aligner.cpp:115-124).  On one device a chunk that
+  // does not fit is STREAMED instead - read, upload, align, release, per query chunk - so a db larger
+  // than device memory still runs; with several devices everything must fit (checked, loud error).
   std::vector<DbChunk> names(info.division);
+  std::vector<char> resident(info.division, 0);
   const uint32_t n_chunks = (uint32_t)info.division;
+  auto upload = [&](gm_context *ctx, uint32_t c, const DbChunk &full) {
+    check(gm_db_upload(ctx, c, full.seq.data(), full.seq_len, full.keys_count.data(),
+                       (uint32_t)full.keys_count.size(), full.positions.data(), (uint32_t)full.positions.size(),
+                       full.seq_starts.data(), full.n_seqs), "gm_db_upload");
+  };
   for (int c = 0; c < info.division; ++c) {
     DbChunk full;
     if (!read_db_chunk(o.db, c, &full, true)) {
@@ -399,15 +432,28 @@ int run_aln(int argc, char **argv) {
       return 0;
     }
     const size_t d = (size_t)c % n_dev;
-    check(gm_db_upload(shards[d].front, (uint32_t)c, full.seq.data(), full.seq_len, full.keys_count.data(),
-                       (uint32_t)full.keys_count.size(), full.positions.data(), (uint32_t)full.positions.size(),
-                       full.seq_starts.data(), full.n_seqs), "gm_db_upload");
-    if (n_dev > 1)
-      for (auto &sh : shards)
-        check(gm_db_upload_seq(sh.back, (uint32_t)c, full.seq.data(), full.seq_len, full.seq_starts.data(),
-                               full.n_seqs), "gm_db_upload_seq");
+    uint64_t free_bytes = 0, total_bytes = 0;
+    check(gm_device_memory(shards[d].front, &free_bytes, &total_bytes), "gm_device_memory");
+    // residues + CSR index + .pos table + the per-key tile boundaries the seed search adds, and a
+    // reserve for candidates, hit lists and the query chunk
+    const uint64_t need = (uint64_t)full.seq_len + 4ull * full.keys_count.size() * 65 + 4ull * full.positions.size() +
+                          4ull * full.n_seqs + (n_dev > 1 ? (uint64_t)full.seq_len * n_dev : 0);
+    // GHOSTM_B200_STREAM=1 forces the streaming path (tests)
+    const bool fits = free_bytes > need + (12ull << 30) && !(n_dev == 1 && getenv("GHOSTM_B200_STREAM"));
+    if (fits) {
+      upload(shards[d].front, (uint32_t)c, full);
+      resident[c] = 1;
+      if (n_dev > 1)
+        for (auto &sh : shards)
+          check(gm_db_upload_seq(sh.back, (uint32_t)c, full.seq.data(), full.seq_len, full.seq_starts.data(),
+                                 full.n_seqs), "gm_db_upload_seq");
+    } else if (n_dev > 1) {
+      throw DeviceError("db chunk " + std::to_string(c) + " does not fit the devices' memory (several devices keep "
+                        "the whole db resident; use one device to stream it)");
+    }
     names[c].names.swap(full.names);
-    if (o.verbose) std::cout << "  db chunk " << c << " -> device " << o.devices[d] << std::endl;
+    if (o.verbose)
+      std::cout << "  db chunk " << c << " -> device " << o.devices[d] << (fits ? "" : " (streamed)") << std::endl;
   }
   // query chunks (query_reader.cpp:50-101, aligner.cpp:98-104,201-203)
   std::ifstream qinf((o.queries + ".inf").c_str(), std::ios::binary);
@@ -425,21 +471,46 @@ int run_aln(int argc, char **argv) {
       const uint64_t budget = std::min<uint64_t>((uint64_t)q.n * 2048 + (1u << 22), (1ull << 32) - 1);
       std::vector<gm_hit> hits((size_t)q.n * cap, gm_hit());
       std::vector<uint32_t> counts(q.n, 0);
+      auto report = [&](uint32_t c, const gm_stats &st, double wall) {   // aligner.cpp:132-159
+        std::cout << "|db chunk " << c << ": " << wall << " sec." << std::endl
+                  << "|  Search alignment candidates ... " << st.ms_search * 1e-3f << " sec. (" << st.candidates
+                  << " candidates in " << st.candidate_chunks << " chunk(s))" << std::endl
+                  << "|  Calculate scores ... " << st.ms_score * 1e-3f << " sec." << std::endl
+                  << "|  Merge results ... " << (st.ms_merge + st.ms_traceback) * 1e-3f << "sec" << std::endl;
+      };
       if (n_dev == 1) {
         gm_context *ctx = shards[0].front;
-        check(gm_set_candidate_capacity(ctx, budget), "gm_set_candidate_capacity");
+        uint64_t capacity = std::max(budget, shards[0].capacity);
+        shards[0].capacity = capacity;
+        check(gm_set_candidate_capacity(ctx, capacity), "gm_set_candidate_capacity");
         check(gm_query_upload(ctx, q.seqs.data(), q.n, q.length, name_break.data()), "gm_query_upload");
-        for (uint32_t c = 0; c < n_chunks; ++c) check(gm_align_chunk(ctx, c, nullptr), "gm_align_chunk");
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+          if (!resident[c]) {     // streamed chunk: like the reference, read and uploaded per query chunk
+            DbChunk full;
+            if (!read_db_chunk(o.db, (int)c, &full, true)) throw std::runtime_error("db chunk file vanished");
+            upload(ctx, c, full);
+          }
+          gm_stats st;
+          memset(&st, 0, sizeof(st));
+          const clock_t t0 = clock();
+          with_capacity_retry(ctx, &shards[0].capacity, "gm_align_chunk", [&] {
+            memset(&st, 0, sizeof(st));
+            return gm_align_chunk(ctx, c, &st);
+          });
+          if (o.verbose) report(c, st, (double)(clock() - t0) / CLOCKS_PER_SEC);
+          if (!resident[c]) check(gm_db_release(ctx, c), "gm_db_release");   // traces its pending hits first
+        }
         check(gm_results_download(ctx, hits.data(), counts.data()), "gm_results_download");
       } else {
         const std::vector<uint32_t> bounds = slice_bounds(name_break, q.n, n_dev);
         on_every_device(shards, [&](size_t d) {
           Shard &sh = shards[d];
           const uint32_t base = bounds[d], stop = bounds[d + 1];
-          check(gm_set_candidate_capacity(sh.front, budget), "gm_set_candidate_capacity");
+          sh.capacity = std::max(budget, sh.capacity);
+          check(gm_set_candidate_capacity(sh.front, sh.capacity), "gm_set_candidate_capacity");
           check(gm_query_upload(sh.front, q.seqs.data(), q.n, q.length, name_break.data()), "gm_query_upload");
           if (stop > base) {
-            check(gm_set_candidate_capacity(sh.back, budget), "gm_set_candidate_capacity");
+            check(gm_set_candidate_capacity(sh.back, sh.capacity), "gm_set_candidate_capacity");
             check(gm_query_upload(sh.back, q.seqs.data() + (size_t)base * q.length, stop - base, q.length,
                                   name_break.data() + base), "gm_query_upload");
           }
@@ -448,8 +519,16 @@ int run_aln(int argc, char **argv) {
           on_every_device(shards, [&](size_t d) {          // front: the owned chunk of this round
             const uint32_t c = round0 + (uint32_t)d;
             shards[d].segs.clear();
-            if (c < n_chunks) shards[d].segs = front_chunk(shards[d].front, c, q.n, o.max_list_length);
+            memset(&shards[d].stats, 0, sizeof(gm_stats));
+            const clock_t t0 = clock();
+            if (c < n_chunks)
+              shards[d].segs = front_chunk(shards[d].front, c, q.n, o.max_list_length, &shards[d].capacity,
+                                           &shards[d].stats);
+            (void)t0;
           });
+          if (o.verbose)
+            for (size_t d = 0; d < n_dev; ++d)
+              if (round0 + d < n_chunks) report(round0 + (uint32_t)d, shards[d].stats, 0.0);
           on_every_device(shards, [&](size_t r) {          // back: the round's chunks, ascending
             const uint32_t base = bounds[r], stop = bounds[r + 1];
             if (stop == base) return;
@@ -459,6 +538,8 @@ int run_aln(int argc, char **argv) {
               if (shards[s].segs.empty()) continue;        // empty list: no Merge call (aligner.cpp:136)
               {
                 std::lock_guard<std::mutex> lock(shards[s].front_mu);
+                uint64_t back_cap = std::max(shards[r].capacity, shards[s].capacity);
+                check(gm_set_candidate_capacity(shards[r].back, back_cap), "gm_set_candidate_capacity");
                 check(gm_candidates_transfer(shards[s].front, shards[r].back, c, base, stop),
                       "gm_candidates_transfer");
               }
@@ -507,8 +588,14 @@ int main(int argc, char **argv) {
     usage();
     return 1;
   }
-  try {  // main.cpp:107-121: errors are reported, the exit status stays 0 like the reference
+  try {  // main.cpp:107-121: usage errors are reported, the exit status stays 0 like the reference
     return run_aln(argc - 1, argv + 1);
+  } catch (DeviceError &e) {
+    // a device-side failure (CUDA error, out of memory, buffer limit) must not look like a finished
+    // run: the partial output file is removed and the status is non-zero
+    std::cerr << "error: " << e.what() << std::endl;
+    if (!g_output_path.empty()) remove(g_output_path.c_str());
+    return 2;
   } catch (std::exception &e) {
     std::cerr << "error: " << e.what() << std::endl;
     return 0;

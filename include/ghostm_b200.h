@@ -138,6 +138,9 @@ const char *gm_version(void);
 const char *gm_last_error(void);
 
 int gm_device_count(void);
+/* Free and total bytes of the context's device (drivers decide with it whether all db chunks stay
+ * resident or are streamed chunk by chunk like the reference does, aligner.cpp:115-173). */
+int gm_device_memory(gm_context *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
 int gm_create(int device, gm_context **ctx);
 void gm_destroy(gm_context *ctx);
 

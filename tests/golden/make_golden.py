@@ -13,7 +13,7 @@ the final hit lists, and `ghostm aln -y 0/1/2` writes the output text.  Stored p
   out_y0.txt out_y1.txt out_y2.txt
   meta.json              aln options
 
-usage: python tests/golden/make_golden.py
+usage: python tests/golden/make_golden.py [case ...]
 """
 import gzip, json, os, shutil, subprocess, sys, tempfile
 
@@ -32,7 +32,12 @@ def run(*a, env=None):
     subprocess.check_call(list(a), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=e)
 
 
+ONLY = set(sys.argv[1:])     # optional: regenerate just the named cases
+
+
 def make_case(name, db_fasta, q_fasta, qry_args, db_args, aln_args, max_list=None, l1024=False):
+    if ONLY and name not in ONLY:
+        return
     out = os.path.join(HERE, name)
     shutil.rmtree(out, ignore_errors=True)
     os.makedirs(out)
@@ -110,6 +115,12 @@ def main():
         qs, qn = synth.queries_from_db(4, dbs, 12, 400, min_length=150)
         make_case("long_queries_l1024", fasta(tmp, "l.fa", dbn, dbs, 60), fasta(tmp, "lq.fa", qn, qs),
                   ["-l", "400"], [], [], l1024=True)
+        # 6. config 4's upper end: ragged queries of 300..1000 residues X-padded to 1000 (`qry -l 1000`,
+        #    13 SW strips of 80 rows, list_len 499), two db chunks
+        dbs, dbn = synth.protein_db(7, 1_300_000)
+        qs, qn = synth.queries_from_db(8, dbs, 6, 1000, min_length=300)
+        make_case("long_queries_l1000", fasta(tmp, "m.fa", dbn, dbs, 60), fasta(tmp, "mq.fa", qn, qs),
+                  ["-l", "1000"], ["-l", "1"], [], l1024=True)
 
 
 if __name__ == "__main__":

@@ -59,7 +59,8 @@ def _check_properties(counts, ids, cand, hits, hit_counts, best):
     return off
 
 
-def _oracle_sample(ctx, db, queries, sample, opt, counts, ids, cand, hits, hit_counts, max_sw=4000):
+def _oracle_sample(ctx, db, queries, sample, opt, counts, ids, cand, hits, hit_counts, max_sw=4000,
+                   sw_sample=None):
     """Exact comparison of the sampled queries against the oracle."""
     chunk = db.chunks[0]
     off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
@@ -69,7 +70,7 @@ def _oracle_sample(ctx, db, queries, sample, opt, counts, ids, cand, hits, hit_c
         assert np.array_equal(ref, got), (q, ref.shape, got.shape)
     # SW scores/ends of (a bounded number of) the sample's candidates
     scores, ends = ctx.score(0, queries.shape[0], int(counts.sum()))
-    for q in sample:
+    for q in (sample if sw_sample is None else sw_sample):
         n = min(int(counts[q]), max_sw)
         if n == 0:
             continue
@@ -116,9 +117,11 @@ def test_config3_full_chunk():
     ctx.align_chunk(0)
     hits, hit_counts = ctx.results()
     _check_properties(counts, ids, cand, hits, hit_counts, opt.best)
-    sample = np.sort(np.random.default_rng(33).choice(n_q, size=24, replace=False))
+    # candidates and hit lists of 256 sampled queries against the oracle on the FULL chunk; SW scores
+    # and ends of a sub-sample (every candidate of 32 queries)
+    sample = np.sort(np.random.default_rng(33).choice(n_q, size=256, replace=False))
     ctx.search(0)
-    _oracle_sample(ctx, db, queries, sample, opt, counts, ids, cand, hits, hit_counts)
+    _oracle_sample(ctx, db, queries, sample, opt, counts, ids, cand, hits, hit_counts, sw_sample=sample[::8])
     _oracle_hit_lists(db, queries, sample, opt, hits, hit_counts)
     ctx.close()
 
@@ -144,6 +147,8 @@ def test_config4_long_queries_full_chunk():
     sample = np.array([0, n_q // 2, n_q - 1])
     ctx.search(0)
     _oracle_sample(ctx, db, queries, sample, opt, counts, ids, cand, hits, hit_counts, max_sw=300)
+    # the final hit lists of two queries (all their candidates through SW, Merge and TraceBack)
+    _oracle_hit_lists(db, queries, sample[:2], opt, hits, hit_counts)
     ctx.close()
 
 
@@ -168,4 +173,5 @@ def test_config5_repeats_full_chunk():
     sample = np.sort(np.array([order[0], order[n_q // 4], order[n_q // 2]]))
     ctx.search(0)
     _oracle_sample(ctx, db, queries, sample, opt, counts, ids, cand, hits, hit_counts, max_sw=2000)
+    _oracle_hit_lists(db, queries, sample[:2], opt, hits, hit_counts)
     ctx.close()

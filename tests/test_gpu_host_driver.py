@@ -4,7 +4,10 @@
     and query slices spread over several shards of one device and - when two are visible - over
     two devices;
   * oracle/_ref/ghostm_dropin = the UNMODIFIED reference host objects linked against
-    libghostm_b200.so: `aln -D 0` drives the ten legacy symbols exactly as the reference does."""
+    libghostm_b200.so: `aln -D 0` drives the ten legacy symbols exactly as the reference does;
+  * oracle/_ref/ghostm_fast = the reference host with ONLY Aligner::Execute replaced by
+    integration/aligner_b200.cpp (gm_* API): readers, SetOption, Statistics and WriteOutput* are the
+    reference's own objects."""
 import os
 import shutil
 import subprocess
@@ -18,6 +21,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ALN = os.path.join(ROOT, "ghostm_b200", "ghostm_b200_aln")
 DROPIN = os.path.join(ROOT, "oracle", "_ref", "ghostm_dropin")
+FAST = os.path.join(ROOT, "oracle", "_ref", "ghostm_fast")
 
 
 def _materialise(name, tmp_path):
@@ -38,7 +42,8 @@ def _gpu_count():
 
 
 @pytest.mark.parametrize("name", ["readme_known_answer", "testset_literal", "synth_groups",
-                                  "synth_two_chunks", "synth_options"])
+                                  "synth_two_chunks", "synth_options", "long_queries_l1024",
+                                  "long_queries_l1000"])
 def test_host_driver_output_files(name, tmp_path):
     assert os.path.exists(ALN), "build with make -C ghostm_b200/csrc"
     meta, texts = _materialise(name, tmp_path)
@@ -53,6 +58,30 @@ def test_host_driver_output_files(name, tmp_path):
             assert open(out, encoding="latin-1", newline="").read() == expect, (name, dev, y)
 
 
+def test_host_driver_streams_chunks_that_do_not_fit(tmp_path):
+    """One device, db chunks not kept resident (forced): read, upload, align, release per query
+    chunk like the reference (aligner.cpp:115-173) - same output bytes; -v reports the phases."""
+    meta, texts = _materialise("synth_two_chunks", tmp_path)
+    env = dict(os.environ, GHOSTM_B200_STREAM="1")
+    for y, expect in texts.items():
+        out = tmp_path / f"stream_{y}.txt"
+        r = subprocess.run([ALN, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o", str(out),
+                            "-D", "0", "-y", str(y), "-v"] + meta["aln_args"], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "(streamed)" in r.stdout and "Calculate scores ..." in r.stdout
+        assert open(out, encoding="latin-1", newline="").read() == expect, y
+
+
+def test_host_driver_device_error_is_not_a_finished_run(tmp_path):
+    """A device-side failure gives a non-zero exit status and leaves no partial output file."""
+    meta, _ = _materialise("synth_groups", tmp_path)
+    out = tmp_path / "out.txt"
+    r = subprocess.run([ALN, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o", str(out),
+                        "-D", "99"], capture_output=True, text=True)
+    assert r.returncode != 0 and "error" in r.stderr
+    assert not out.exists()
+
+
 @pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref/ghostm_dropin not built")
 @pytest.mark.parametrize("name", ["readme_known_answer", "synth_groups", "synth_two_chunks"])
 def test_reference_host_linked_against_our_library(name, tmp_path):
@@ -62,6 +91,23 @@ def test_reference_host_linked_against_our_library(name, tmp_path):
     subprocess.check_call([DROPIN, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o", str(out),
                            "-D", "0", "-l", "1"] + meta["aln_args"])
     assert open(out, encoding="latin-1", newline="").read() == texts[0]
+
+
+@pytest.mark.skipif(not os.path.exists(FAST), reason="oracle/_ref/ghostm_fast not built")
+@pytest.mark.parametrize("name", ["readme_known_answer", "testset_literal", "synth_groups",
+                                  "synth_two_chunks", "synth_options", "long_queries_l1024",
+                                  "long_queries_l1000"])
+def test_reference_host_with_execute_on_gm_api(name, tmp_path):
+    """The reference binary with Aligner::Execute swapped for integration/aligner_b200.cpp: same
+    output bytes as the golden reference text for -y 0/1/2; -v prints the per-phase times."""
+    meta, texts = _materialise(name, tmp_path)
+    for y, expect in texts.items():
+        out = tmp_path / f"fast_{y}.txt"
+        r = subprocess.run([FAST, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o", str(out),
+                            "-D", "0", "-y", str(y), "-v"] + meta["aln_args"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, encoding="latin-1", newline="").read() == expect, (name, y)
+        assert "Calculate scores ..." in r.stdout and "Merge results ..." in r.stdout and "Complete." in r.stdout
 
 
 REF = os.path.join(ROOT, "oracle", "_ref", "ghostm")
@@ -108,3 +154,7 @@ def test_config2_standin_against_the_live_reference(n_reads, style, tmp_path):
         subprocess.check_call([ALN, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o",
                                str(tmp_path / "ours.txt"), "-D", dev, "-y", style], **quiet)
         assert (tmp_path / "ours.txt").read_bytes() == ref, dev
+    if os.path.exists(FAST):     # the reference host with Execute on the gm_* API, same files
+        subprocess.check_call([FAST, "aln", "-i", str(tmp_path / "q"), "-d", str(tmp_path / "db"), "-o",
+                               str(tmp_path / "fast.txt"), "-D", "0", "-y", style], **quiet)
+        assert (tmp_path / "fast.txt").read_bytes() == ref
