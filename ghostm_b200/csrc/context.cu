@@ -7,7 +7,6 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
 
 #include "gm_common.cuh"
 
@@ -30,6 +29,10 @@ bool search_tile_geometry(uint32_t threshold, uint32_t list_len, uint32_t shift,
                           uint32_t seq_len, uint32_t n_keys, size_t smem_per_sm, TileGeometry *g);
 int search_tile_grid(int sm_count);
 size_t search_tile_emap_words(const TileGeometry &g);
+size_t index_sort_scratch_words(uint32_t n);
+cudaError_t index_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp,
+                             uint32_t *vals_final, uint32_t n, uint32_t bits, uint32_t *scratch,
+                             uint32_t **sorted_keys, uint32_t *launches, cudaStream_t stream);
 cudaError_t search_split_build(const uint32_t *keys_count, uint32_t n_keys, const uint32_t *positions,
                                const TileGeometry &g, uint32_t *split, int sm_count, cudaStream_t stream);
 cudaError_t seed_search_tile_launch(SearchParams p, const TileGeometry &g, int sm_count,
@@ -1326,27 +1329,28 @@ extern "C" int gm_db_build_index(gm_context *c, uint32_t id, const uint8_t *seq,
   GM_CUDA(ch.positions.ensure(seq_len));
   GM_CUDA(cudaMemcpyAsync(ch.seq.p, seq, seq_len, cudaMemcpyHostToDevice, c->stream));
   GM_CUDA(cudaMemcpyAsync(ch.seq_starts.p, seq_starts, (size_t)n_seqs * 4, cudaMemcpyHostToDevice, c->stream));
-  DevBuf<uint32_t> keys, keys_sorted, pos;
-  DevBuf<unsigned char> temp;
+  // db_creator.cpp:167-241: keys of all offsets, then the stable counting sort of index_build.cu
+  // (hand-written, 8-bit passes over one bit more than the key width: the 0xFFFFFFFF keys of
+  // non-indexable offsets end up last), then the CSR boundaries
+  DevBuf<uint32_t> keys, keys_tmp, pos, pos_tmp, scratch;
   GM_CUDA(keys.ensure(seq_len));
-  GM_CUDA(keys_sorted.ensure(seq_len));
+  GM_CUDA(keys_tmp.ensure(seq_len));
   GM_CUDA(pos.ensure(seq_len));
+  GM_CUDA(pos_tmp.ensure(seq_len));
+  GM_CUDA(scratch.ensure(index_sort_scratch_words(seq_len)));
   index_keys_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(ch.seq.p, seq_len, ch.seq_starts.p, n_seqs,
                                                             seed, seed_length_of(seed), keys.p, pos.p);
   GM_CUDA(cudaGetLastError());
-  size_t temp_bytes = 0;
-  GM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys.p, keys_sorted.p, pos.p,
-                                          ch.positions.p, (int)seq_len, 0, 32, c->stream));
-  GM_CUDA(temp.ensure(temp_bytes));
-  GM_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, keys.p, keys_sorted.p, pos.p,
-                                          ch.positions.p, (int)seq_len, 0, 32, c->stream));
-  index_bounds_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(keys_sorted.p, seq_len, n_keys,
+  uint32_t *keys_sorted = nullptr;
+  GM_CUDA(index_sort_pairs(keys.p, pos.p, keys_tmp.p, pos_tmp.p, ch.positions.p, seq_len,
+                           kCharBits * weight + 1, scratch.p, &keys_sorted, nullptr, c->stream));
+  index_bounds_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(keys_sorted, seq_len, n_keys,
                                                               ch.keys_count.p);
   GM_CUDA(cudaGetLastError());
   uint32_t n_pos = 0;
   GM_CUDA(cudaMemcpyAsync(&n_pos, ch.keys_count.p + n_keys, 4, cudaMemcpyDeviceToHost, c->stream));
   GM_CUDA(cudaStreamSynchronize(c->stream));
-  keys.release(); keys_sorted.release(); pos.release(); temp.release();
+  keys.release(); keys_tmp.release(); pos.release(); pos_tmp.release(); scratch.release();
   ch.seq_len = seq_len;
   ch.n_seqs = n_seqs;
   ch.keys_count_len = n_keys + 1;

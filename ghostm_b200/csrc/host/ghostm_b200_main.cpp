@@ -574,22 +574,174 @@ int run_aln(int argc, char **argv) {
   return 0;
 }
 
+// ---- `db`: FASTA -> <prefix>.inf, <prefix>_<i>.{inf,nam,seq,pos,ind} ----------------------------
+// Same bytes as the reference's `ghostm db` (db_creator.cpp:369-479); the counting sort behind the
+// index (db_creator.cpp:167-241, one host thread there) runs on the device (gm_db_build_index).
+struct FastaReader {     // fasta_sequence_reader.cpp:34-86
+  std::ifstream in;
+  std::string last_line;
+  explicit FastaReader(const std::string &path) : in(path.c_str()) {}
+  bool next(std::string *name, std::string *residues) {
+    if (in.eof()) return false;
+    std::string line = last_line;
+    while (!in.eof() && (line.empty() || line[0] != '>')) std::getline(in, line);
+    if (in.eof()) return false;
+    if (line[line.size() - 1] == '\r') line.erase(line.size() - 1);
+    name->clear();
+    const size_t at = line.find_first_not_of("> ");
+    if (at != std::string::npos) *name = line.substr(at);
+    residues->clear();
+    while (!in.eof()) {
+      std::getline(in, line);
+      if (line.empty()) continue;
+      if (line[0] == '>') break;
+      if (line[line.size() - 1] == '\r') line.erase(line.size() - 1);
+      if (!line.empty() && line[line.size() - 1] == '+') line.erase(line.size() - 1);
+      *residues += line;
+    }
+    last_line = line;
+    return true;
+  }
+};
+
+template <typename T>
+void write_raw(std::ofstream &out, const T *p, size_t n) {
+  out.write(reinterpret_cast<const char *>(p), (std::streamsize)(n * sizeof(T)));
+}
+
+int run_db(int argc, char **argv) {
+  std::string input, prefix;
+  uint32_t seed = (1u << 4) - 1, max_len = 1u << 27;     // db_creator.cpp:57-58
+  int device = 0, c;
+  while ((c = getopt(argc, argv, "i:o:k:l:D:")) >= 0) {
+    switch (c) {
+      case 'i': input = optarg; break;
+      case 'o': prefix = optarg; break;
+      case 'k': seed = (1u << atoi(optarg)) - 1; break;            // contiguous seed of weight k
+      case 'l': max_len = (uint32_t)(atoi(optarg) * (1 << 20)); break;
+      case 'D': device = atoi(optarg); break;                      // (not a reference option)
+      default: throw std::invalid_argument("");
+    }
+  }
+  std::cerr << "seed : " << seed << std::endl << "max length :" << max_len << std::endl;
+  gm_context *ctx = nullptr;
+  check(gm_create(device, &ctx), "gm_create");
+  uint32_t weight = 0;
+  for (uint32_t s = seed; s; s >>= 1) weight += s & 1;
+  const uint32_t keys_count_len = (1u << (5 * weight)) + 1;
+
+  FastaReader reader(input);
+  std::string name, residues, next_name, next_residues;
+  bool have_next = false;
+  uint64_t sum_length = 0;
+  int division = 0;
+  for (;; ++division) {
+    // db_creator.cpp:88-132: sequences are added while residues + separators fit max_len; the one
+    // that does not fit opens the next chunk
+    std::vector<std::string> names;
+    std::vector<uint8_t> seq;
+    std::vector<uint32_t> starts;
+    uint32_t sum = 0;
+    if (have_next) {
+      sum = (uint32_t)next_residues.size() + 1;
+      if (sum > max_len) {
+        std::cerr << "error : too small max length." << std::endl;
+        gm_destroy(ctx);
+        return 1;
+      }
+      names.push_back(next_name);
+      starts.push_back(0);
+      for (char ch : next_residues) seq.push_back((uint8_t)residue_code(ch));
+      seq.push_back(25);
+      have_next = false;
+    }
+    while (reader.next(&name, &residues)) {
+      sum += (uint32_t)residues.size() + 1;
+      if (sum > max_len) {
+        next_name = name;
+        next_residues = residues;
+        have_next = true;
+        sum -= (uint32_t)residues.size() + 1;
+        break;
+      }
+      names.push_back(name);
+      starts.push_back((uint32_t)seq.size());
+      for (char ch : residues) seq.push_back((uint8_t)residue_code(ch));
+      seq.push_back(25);                                          // SEQUENCE_END, db_creator.cpp:138-159
+    }
+    std::cerr << "sum length : " << sum << std::endl;
+    if (names.empty()) break;
+    sum_length += seq.size() - names.size();
+    std::ostringstream sub;
+    sub << prefix << "_" << division;
+    {
+      std::ofstream out((sub.str() + ".inf").c_str(), std::ios::binary);
+      const uint32_t n = (uint32_t)names.size(), len = (uint32_t)seq.size();
+      write_raw(out, &n, 1);
+      write_raw(out, &len, 1);
+    }
+    {
+      std::ofstream out((sub.str() + ".nam").c_str());
+      for (const std::string &nm : names) out << nm << std::endl;
+    }
+    {
+      std::ofstream out((sub.str() + ".seq").c_str(), std::ios::binary);
+      write_raw(out, seq.data(), seq.size());
+    }
+    {
+      std::ofstream out((sub.str() + ".pos").c_str(), std::ios::binary);
+      write_raw(out, starts.data(), starts.size());
+    }
+    // the index: keys, stable counting sort and CSR boundaries on the device
+    check(gm_db_build_index(ctx, 0, seq.data(), (uint32_t)seq.size(), starts.data(), (uint32_t)starts.size(), seed),
+          "gm_db_build_index");
+    std::vector<uint32_t> keys_count(keys_count_len), positions(seq.size());
+    uint32_t n_pos = 0;
+    check(gm_db_download_index(ctx, 0, keys_count.data(), positions.data(), &n_pos), "gm_db_download_index");
+    {
+      std::ofstream out((sub.str() + ".ind").c_str(), std::ios::binary);   // db_creator.cpp:332-352
+      write_raw(out, &seed, 1);
+      write_raw(out, &keys_count_len, 1);
+      write_raw(out, &n_pos, 1);
+      write_raw(out, keys_count.data(), keys_count.size());
+      write_raw(out, positions.data(), n_pos);
+    }
+    check(gm_db_release(ctx, 0), "gm_db_release");
+    std::cerr << "number sequences : " << names.size() << std::endl;
+  }
+  std::cerr << "[db] division number : " << division << std::endl;
+  {
+    std::ofstream out((prefix + ".inf").c_str(), std::ios::binary);       // db_creator.cpp:243-264
+    const int32_t div = division;
+    write_raw(out, &div, 1);
+    write_raw(out, &seed, 1);
+    write_raw(out, &max_len, 1);
+    write_raw(out, &sum_length, 1);
+    for (int i = 0; i < 32; ++i) write_raw(out, &div, 1);
+  }
+  gm_destroy(ctx);
+  return 0;
+}
+
 void usage() {
   std::cerr << "usage: ghostm_b200 aln [-i queries] [-d database] [-o output] [-D device[,device...]]\n"
                "          [-v] [-b best] [-G openGap] [-E extendGap] [-M scoreMatrix] [-l candidatesMB]\n"
                "          [-s skip] [-t threshold] [-r regionSize] [-e extendSize] [-S first] [-L last] [-y style]\n"
-               "   `db` and `qry` formatting stay with the reference tool; the file formats are unchanged.\n";
+               "       ghostm_b200 db [-i fasta] [-o database] [-k seedWeight] [-l chunkMB] [-D device]\n"
+               "   `db` writes the reference's files byte for byte (index built on the GPU); `qry` formatting\n"
+               "   stays with the reference tool; the file formats are unchanged.\n";
 }
 
 }  // namespace
 
 int main(int argc, char **argv) {
-  if (argc < 2 || strcmp(argv[1], "aln") != 0) {
+  if (argc < 2 || (strcmp(argv[1], "aln") != 0 && strcmp(argv[1], "db") != 0)) {
     usage();
     return 1;
   }
+  const bool is_db = strcmp(argv[1], "db") == 0;
   try {  // main.cpp:107-121: usage errors are reported, the exit status stays 0 like the reference
-    return run_aln(argc - 1, argv + 1);
+    return is_db ? run_db(argc - 1, argv + 1) : run_aln(argc - 1, argv + 1);
   } catch (DeviceError &e) {
     // a device-side failure (CUDA error, out of memory, buffer limit) must not look like a finished
     // run: the partial output file is removed and the status is non-zero

@@ -111,6 +111,51 @@ def test_reference_host_with_execute_on_gm_api(name, tmp_path):
 
 
 REF = os.path.join(ROOT, "oracle", "_ref", "ghostm")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ghostm")),
+                    reason="oracle/_ref/ghostm not built (needs /root/reference)")
+@pytest.mark.parametrize("k", [4, 3])
+def test_db_command_writes_the_reference_files(k, tmp_path):
+    """`ghostm_b200_aln db` (FASTA parsing + chunking on the host, key extraction + hand-written
+    stable counting sort + CSR boundaries on the device) against the reference's `ghostm db`
+    (db_creator.cpp:369-479) on a multi-chunk FASTA with the reader's corner cases: every output
+    file byte-identical."""
+    import numpy as np
+    from ghostm_b200 import synth
+    rng = np.random.default_rng(77)
+    dbs, dbn = synth.protein_db(78, 2_400_000)
+    letters = "ARNDCQEGHILKMFPSTWYVBJZX*"
+    with open(tmp_path / "db.fa", "w", newline="") as f:
+        f.write("junk before the first header\n")
+        for i, (s, nm) in enumerate(zip(dbs, dbn)):
+            txt = "".join(letters[int(c)] for c in s)
+            if i % 7 == 0:
+                txt = txt.lower()
+            if i % 11 == 0:
+                txt = txt[:20] + "XX-U" + txt[20:]          # X, and characters that map to X
+            if i % 13 == 0:
+                txt = txt[: int(rng.integers(1, 6))]       # not longer than the seed: not indexed
+            eol = "\r\n" if i % 5 == 0 else "\n"
+            head = (">  " if i % 3 == 0 else ">") + nm + (" some description" if i % 4 == 0 else "")
+            f.write(head + eol)
+            for a in range(0, len(txt), 60):
+                f.write(txt[a:a + 60] + ("+" if i % 17 == 0 else "") + eol)
+            if i % 19 == 0:
+                f.write("\n")
+    quiet = dict(stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call([REF, "db", "-i", str(tmp_path / "db.fa"), "-o", str(tmp_path / "ref"), "-l", "1",
+                           "-k", str(k)], **quiet)
+    subprocess.check_call([ALN, "db", "-i", str(tmp_path / "db.fa"), "-o", str(tmp_path / "ours"), "-l", "1",
+                           "-k", str(k)], **quiet)
+    ref_files = sorted(f for f in os.listdir(tmp_path) if f.startswith("ref"))
+    assert len(ref_files) >= 1 + 5 * 3, ref_files
+    for f in ref_files:
+        ours = tmp_path / ("ours" + f[3:])
+        assert ours.exists(), f
+        assert ours.read_bytes() == (tmp_path / f).read_bytes(), f
+
+
 _CODON = ["GCT", "CGT", "AAT", "GAT", "TGT", "CAA", "GAA", "GGT", "CAT", "ATT", "CTT", "AAA", "ATG",
           "TTT", "CCT", "TCT", "ACT", "TGG", "TAT", "GTT"]   # one codon per residue code A..V
 
