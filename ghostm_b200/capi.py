@@ -28,7 +28,8 @@ EXTENDED_SYMBOLS = ["gm_version", "gm_last_error", "gm_device_count", "gm_create
                     "gm_results_device", "gm_stream", "gm_measure_dpx_peak",
                     "gm_set_deferred_traceback", "gm_traceback_pending", "gm_set_search_variant",
                     "gm_align_prepare", "gm_align_merge", "gm_db_upload_seq", "gm_candidates_pack",
-                    "gm_candidates_import", "gm_candidates_transfer", "gm_device_memory"]
+                    "gm_candidates_import", "gm_candidates_transfer", "gm_device_memory",
+                    "gm_query_upload_async", "gm_align_chunk_async", "gm_results_download_async", "gm_wait"]
 
 HIT_DTYPE = np.dtype([("query_id", "<u4"), ("db_id", "<u4"), ("db_chunk", "<u4"), ("score", "<u4"),
                       ("db_start", "<u4"), ("db_end", "<u4"), ("aln_len", "<u4"),
@@ -90,6 +91,11 @@ def load():
     L.gm_align_prepare.argtypes = [vp, C.c_uint32, C.POINTER(GmStats)]
     L.gm_align_merge.argtypes = [vp, C.POINTER(GmStats)]
     L.gm_results_download.argtypes = [vp, vp, vp]
+    L.gm_results_download_async.argtypes = [vp, vp, vp]
+    L.gm_query_upload_async.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
+    L.gm_align_chunk_async.argtypes = [vp, C.c_uint32]
+    L.gm_wait.argtypes = [vp, C.POINTER(GmStats)]
+    L.gm_device_memory.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.gm_results_upload.argtypes = [vp, vp, vp]
     L.gm_search.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_uint64), C.POINTER(GmStats)]
     L.gm_chunk_rule.restype = C.c_uint32
@@ -269,6 +275,19 @@ class Context:
 
     def align_merge(self, stats: Optional[GmStats] = None):
         self._check(self.L.gm_align_merge(self.h, C.byref(stats) if stats is not None else None))
+
+    def align_chunk_async(self, chunk_id: int):
+        self._check(self.L.gm_align_chunk_async(self.h, chunk_id))
+
+    def wait(self, stats: Optional[GmStats] = None):
+        self._check(self.L.gm_wait(self.h, C.byref(stats) if stats is not None else None))
+
+    def query_upload_async_ptr(self, ptr: int, n: int, length: int, name_break_ptr: int = 0):
+        self._check(self.L.gm_query_upload_async(self.h, ptr, n, length, name_break_ptr or None))
+        self.n_queries = n
+
+    def results_download_async_ptr(self, hits_ptr: int, counts_ptr: int):
+        self._check(self.L.gm_results_download_async(self.h, hits_ptr, counts_ptr))
 
     def results(self):
         hits = np.zeros((self.n_queries, self.cap), dtype=HIT_DTYPE)

@@ -146,6 +146,23 @@ __global__ void pack_kernel(const uint32_t *cand_off, const uint32_t *cand_cnt,
   }
 }
 
+// After the seed search of an asynchronously enqueued chunk: the host never sees the counts, so the
+// conditions it would act on are recorded on the device.  One candidate chunk covers all queries
+// iff the total does not exceed the budget -l (aligner.cpp:511-516).
+__global__ void async_check_kernel(const unsigned long long *cursor, const unsigned long long *visited,
+                                   const int *overflow, unsigned long long max_list_length,
+                                   unsigned long long *ctr, uint32_t *flag) {
+  if (*cursor > max_list_length || *overflow) flag[0] = 1;
+  ctr[1] += *visited;
+  ctr[2] += *cursor;
+}
+
+__global__ void async_cells_kernel(const unsigned long long *cells, const uint32_t *merge_error,
+                                   unsigned long long *ctr, uint32_t *flag) {
+  ctr[0] += *cells;
+  if (*merge_error) flag[1] = 1;
+}
+
 // db_creator.cpp:167-241 on the device: key of every indexable position (or 0xFFFFFFFF).
 __global__ void index_keys_kernel(const uint8_t *seq, uint32_t seq_len, const uint32_t *seq_starts,
                                   uint32_t n_seqs, uint32_t seed, uint32_t seed_len, uint32_t *keys,
@@ -233,6 +250,19 @@ struct gm_context {
   size_t smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {};
+  // asynchronous layer (gm_align_chunk_async / gm_wait)
+  std::vector<uint32_t> chunks_since_upload;   // every chunk aligned against the resident queries, in order
+  std::vector<cudaEvent_t> async_ev;           // 4 per enqueued chunk: start, search, score, merge
+  uint32_t async_open = 0;                     // chunks enqueued and not waited for
+  DevBuf<unsigned long long> async_ctr;        // [0] cells [1] index positions [2] candidates (accumulating)
+  DevBuf<uint32_t> async_flag;                 // [0] candidate budget / capacity exceeded [1] merge scratch
+  uint32_t *h_async = nullptr;                 // pinned read-back of flags and counters
+  bool no_sync_upload = false, no_sync_download = false;
+  std::vector<uint32_t> upload_keep, upload_keep2;
+  bool traced_async = false;                   // a TraceBack was enqueued without reading its counters
+  gm_hit *dl_hits = nullptr;                   // host buffers of an enqueued gm_results_download_async
+  uint32_t *dl_counts = nullptr;
+  bool dl_open = false;
 
   bool has_opt = false;
   gm_options opt = {};
@@ -401,6 +431,9 @@ extern "C" void gm_destroy(gm_context *c) {
   c->small.release(); c->hits[0].release(); c->hits[1].release(); c->hit_cnt[0].release();
   c->hit_cnt[1].release(); c->jobs.release(); c->big_scratch.release(); c->tb_work.release(); c->chunk_tab.release();
   for (auto &e : c->ev) cudaEventDestroy(e);
+  for (auto &e : c->async_ev) cudaEventDestroy(e);
+  c->async_ctr.release(); c->async_flag.release();
+  if (c->h_async) cudaFreeHost(c->h_async);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -558,7 +591,9 @@ extern "C" int gm_query_upload(gm_context *c, const uint8_t *seqs, uint32_t n, u
   }
   GM_CUDA(c->jobs.ensure((size_t)n * c->cap));
   GM_CUDA(cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)n * 4, c->stream));
-  GM_CUDA(cudaStreamSynchronize(c->stream));
+  if (!c->no_sync_upload) GM_CUDA(cudaStreamSynchronize(c->stream));
+  else c->upload_keep.swap(first), c->upload_keep2.swap(last);   // the copies read them until the stream gets there
+  c->chunks_since_upload.clear();
   c->cur_hits = 0;
   c->cur_chunk = -1;
   c->cand_total = 0;
@@ -567,8 +602,11 @@ extern "C" int gm_query_upload(gm_context *c, const uint8_t *seqs, uint32_t n, u
   return 0;
 }
 
-extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t *total,
-                         gm_stats *stats) {
+namespace {
+// Seed search of all resident queries against chunk id.  async: nothing comes back to the host and
+// nothing waits - the candidate total and the overflow flag are checked on the device
+// (async_check_kernel); returns 1 when the option set needs a search path with a host decision.
+int search_impl(gm_context *c, uint32_t id, uint32_t *counts, uint64_t *total, gm_stats *stats, bool async) {
   if (int r = check_ctx(c)) return r;
   if (int r = ensure_query_state(c)) return r;
   if (id >= GM_MAX_DB_CHUNKS || !c->chunks[id].valid)
@@ -582,8 +620,11 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
   GM_CUDA(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
   GM_CUDA(cudaMemsetAsync(c->small.p, 0, 8 * sizeof(uint32_t), c->stream));
   c->cur_chunk = -1;
-  c->h_counts.assign(c->n_queries, 0);
+  if (!async) c->h_counts.assign(c->n_queries, 0);
 
+  if (async && (c->opt.threshold == 0 || c->opt.threshold > 2 * c->list_len ||
+                c->opt.threshold > (uint32_t)search_max_threshold()))
+    return 1;
   if (c->opt.threshold == 0 || c->opt.threshold > 2 * c->list_len) {
     // aligner.cpp:416: threshold - 1 wraps to UINT_MAX, `count > threshold` is never true; and
     // cnt(d) + cnt(d+1) <= 2 * list_len (every list counts once per region, aligner.cpp:466-476)
@@ -651,6 +692,7 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
                       search_hash_ok(p.threshold, p.list_len, p.n_regions);
     const bool bucket = !tile && !hash && c->search_bucket && c->search_fast &&
                         search_bucket_ok(p.threshold, p.list_len, p.n_regions, &tile_bits, &bucket_cap);
+    if (async && (hash || bucket)) return 1;   // their over-capacity hand-over is decided on the host
     if (hash) {
       GM_CUDA(c->fallback.ensure(c->n_queries));
       p.fallback_list = c->fallback.p;
@@ -690,6 +732,16 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
     } else {
       GM_CUDA(seed_search_launch(p, grid, c->stream, c->search_fast));
     }
+    if (async) {
+      async_check_kernel<<<1, 1, 0, c->stream>>>(c->counters.p + 0, c->counters.p + 1,
+                                                 reinterpret_cast<const int *>(c->small.p + 2),
+                                                 std::min<unsigned long long>(c->opt.max_list_length, c->cand_capacity),
+                                                 c->async_ctr.p, c->async_flag.p);
+      GM_CUDA(cudaGetLastError());
+      c->cur_chunk = (int)id;
+      c->imported = false;
+      return 0;
+    }
     GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
     GM_CUDA(cudaMemcpyAsync(c->h_counts.data(), c->cand_cnt.p, (size_t)c->n_queries * 4,
                             cudaMemcpyDeviceToHost, c->stream));
@@ -717,6 +769,12 @@ extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t 
   if (counts) memcpy(counts, c->h_counts.data(), (size_t)c->n_queries * 4);
   if (total) *total = sum;
   return 0;
+}
+}  // namespace
+
+extern "C" int gm_search(gm_context *c, uint32_t id, uint32_t *counts, uint64_t *total,
+                         gm_stats *stats) {
+  return search_impl(c, id, counts, total, stats, false);
 }
 
 extern "C" uint32_t gm_chunk_rule(const uint32_t *counts, uint32_t n, uint32_t first_query,
@@ -922,8 +980,9 @@ extern "C" int gm_candidates_transfer(gm_context *src, gm_context *dst, uint32_t
   return 0;
 }
 
-extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *scores,
-                        uint32_t *ends, gm_stats *stats) {
+namespace {
+int score_impl(gm_context *c, uint32_t first, uint32_t end, uint32_t *scores, uint32_t *ends,
+               gm_stats *stats, bool async) {
   if (int r = check_ctx(c)) return r;
   if (int r = check_range(c, first, end, true)) return r;
   if (first == end) return 0;
@@ -970,6 +1029,12 @@ extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *s
     GM_CUDA(sw_extend_s32_launch(p, c->sm_count, c->stream));
     launches = 1;
   }
+  if (async) {   // the SW cells of this launch join the running sum; nothing is read back
+    async_cells_kernel<<<1, 1, 0, c->stream>>>(c->counters.p + 2, c->async_flag.p + 2, c->async_ctr.p,
+                                               c->async_flag.p);
+    GM_CUDA(cudaGetLastError());
+    return 0;
+  }
   GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
   if (scores || ends) {
     uint32_t total = 0;
@@ -1001,6 +1066,12 @@ extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *s
     stats->candidates += n;
   }
   return 0;
+}
+}  // namespace
+
+extern "C" int gm_score(gm_context *c, uint32_t first, uint32_t end, uint32_t *scores,
+                        uint32_t *ends, gm_stats *stats) {
+  return score_impl(c, first, end, scores, ends, stats, false);
 }
 
 namespace {
@@ -1083,6 +1154,13 @@ extern "C" int gm_traceback_pending(gm_context *c, uint64_t *n_done, gm_stats *s
                                  c->sm_count, c->stream));
   if (int r = run_traceback(c, hits)) return r;
   GM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  if (c->no_sync_download) {   // gm_results_download_async: the counts are looked at in gm_wait
+    GM_CUDA(cudaMemcpyAsync(c->h_async + 12, c->small.p + 3, 4, cudaMemcpyDeviceToHost, c->stream));
+    GM_CUDA(cudaMemcpyAsync(c->h_async + 13, c->small.p + 7, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->pending = false;
+    c->traced_async = true;
+    return 0;
+  }
   uint32_t n = 0, left = 0;
   GM_CUDA(cudaMemcpyAsync(&n, c->small.p + 3, 4, cudaMemcpyDeviceToHost, c->stream));
   GM_CUDA(cudaMemcpyAsync(&left, c->small.p + 7, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1100,13 +1178,15 @@ extern "C" int gm_traceback_pending(gm_context *c, uint64_t *n_done, gm_stats *s
   return 0;
 }
 
-extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *stats) {
+namespace {
+int merge_impl(gm_context *c, uint32_t first, uint32_t end, gm_stats *stats, bool async) {
   if (int r = check_ctx(c)) return r;
   if (int r = check_range(c, first, end)) return r;
   DbChunk &ch = c->chunks[c->cur_chunk];
   const int src = c->cur_hits, dst = src ^ 1;
   uint64_t n_new = 0;
-  for (uint32_t q = first; q < end; ++q) n_new += c->h_counts[q];
+  if (async) n_new = std::min<uint64_t>(c->cand_capacity, c->opt.max_list_length);   // the host never saw the counts
+  else for (uint32_t q = first; q < end; ++q) n_new += c->h_counts[q];
   const uint64_t big_cap = 2 * (n_new + (uint64_t)c->n_queries * c->cap) + 2;  // records + stopper positions
   GM_CUDA(c->big_scratch.ensure(big_cap));
   MergeParams p = {};
@@ -1157,6 +1237,13 @@ extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *s
   } else {
     c->pending = true;
   }
+  if (async) {   // the scratch-exhausted flag becomes sticky on the device; gm_wait looks at it
+    async_cells_kernel<<<1, 1, 0, c->stream>>>(c->async_ctr.p + 3, c->small.p + 4, c->async_ctr.p,
+                                               c->async_flag.p);
+    GM_CUDA(cudaGetLastError());
+    c->cur_hits = dst;
+    return 0;
+  }
   GM_CUDA(cudaEventRecord(c->ev[2], c->stream));
   uint32_t small[8];
   GM_CUDA(cudaMemcpyAsync(small, c->small.p, sizeof(small), cudaMemcpyDeviceToHost, c->stream));
@@ -1174,6 +1261,11 @@ extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *s
     stats->candidate_chunks += 1;
   }
   return 0;
+}
+}  // namespace
+
+extern "C" int gm_merge(gm_context *c, uint32_t first, uint32_t end, gm_stats *stats) {
+  return merge_impl(c, first, end, stats, false);
 }
 
 extern "C" int gm_align_prepare(gm_context *c, uint32_t id, gm_stats *stats) {
@@ -1211,8 +1303,163 @@ extern "C" int gm_align_merge(gm_context *c, gm_stats *stats) {
 }
 
 extern "C" int gm_align_chunk(gm_context *c, uint32_t id, gm_stats *stats) {
+  if (c && c->async_open)
+    if (int r = gm_wait(c, stats)) return r;
   if (int r = gm_align_prepare(c, id, stats)) return r;
-  return gm_align_merge(c, stats);
+  if (int r = gm_align_merge(c, stats)) return r;
+  c->chunks_since_upload.push_back(id);
+  return 0;
+}
+
+// ---- asynchronous layer -----------------------------------------------------------------------
+// gm_align_chunk_async enqueues seed search, SW extension and Merge of one db chunk on the
+// context's stream and returns; nothing is copied back and nothing waits.  What the host would
+// decide from the per-query counts - whether the candidate budget -l cuts the chunk into several
+// Merge calls (aligner.cpp:511-516), whether a buffer overflowed - is recorded on the device and
+// looked at once, in gm_wait: if any enqueued chunk needed such a decision, gm_wait redoes the
+// whole batch through the synchronous calls (same results, just slower), so the async path never
+// changes a hit list.  Option sets whose search or Merge needs the host (bucket / hash kernels,
+// best > 16 where an extra Merge call on an unchanged list is not a no-op, immediate TraceBack)
+// fall back to the synchronous call inside gm_align_chunk_async itself.
+namespace {
+
+int async_state(gm_context *c) {
+  if (!c->async_ctr.p) {
+    GM_CUDA(c->async_ctr.ensure(4));
+    GM_CUDA(c->async_flag.ensure(4));
+    GM_CUDA(cudaMemsetAsync(c->async_ctr.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    GM_CUDA(cudaMemsetAsync(c->async_flag.p, 0, 4 * sizeof(uint32_t), c->stream));
+    GM_CUDA(cudaMallocHost(&c->h_async, 16 * sizeof(uint32_t)));
+  }
+  return 0;
+}
+
+cudaEvent_t async_event(gm_context *c, size_t i) {
+  while (c->async_ev.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->async_ev.push_back(e);
+  }
+  return c->async_ev[i];
+}
+
+}  // namespace
+
+extern "C" int gm_align_chunk_async(gm_context *c, uint32_t id) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  if (int r = async_state(c)) return r;
+  const bool eligible = c->deferred && c->opt.best <= 16;
+  if (eligible) {
+    const size_t e0 = (size_t)c->async_open * 4;
+    GM_CUDA(cudaEventRecord(async_event(c, e0), c->stream));
+    const int rs = search_impl(c, id, nullptr, nullptr, nullptr, true);
+    if (rs < 0) return rs;
+    if (rs == 0) {
+      GM_CUDA(cudaEventRecord(async_event(c, e0 + 1), c->stream));
+      if (int r = score_impl(c, 0, c->n_queries, nullptr, nullptr, nullptr, true)) return r;
+      GM_CUDA(cudaEventRecord(async_event(c, e0 + 2), c->stream));
+      if (int r = merge_impl(c, 0, c->n_queries, nullptr, true)) return r;
+      GM_CUDA(cudaEventRecord(async_event(c, e0 + 3), c->stream));
+      c->chunks_since_upload.push_back(id);
+      ++c->async_open;
+      return 0;
+    }
+  }
+  // not eligible: the synchronous call (drains the stream first, order is kept)
+  if (int r = gm_align_chunk(c, id, nullptr)) return r;
+  return 0;
+}
+
+extern "C" int gm_wait(gm_context *c, gm_stats *stats) {
+  if (int r = check_ctx(c)) return r;
+  if (c->async_open == 0) {
+    GM_CUDA(cudaStreamSynchronize(c->stream));
+    const bool traced = c->traced_async;
+    c->traced_async = c->dl_open = false;
+    if (traced && c->h_async[13])
+      return fail(GM_ERR_ARGUMENT, "%u hits cannot be traced back: their db chunk is not resident in this "
+                  "context", c->h_async[13]);
+    return 0;
+  }
+  GM_CUDA(cudaMemcpyAsync(c->h_async, c->async_flag.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaMemcpyAsync(c->h_async + 4, c->async_ctr.p, 4 * sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, c->stream));
+  GM_CUDA(cudaMemsetAsync(c->async_ctr.p, 0, 4 * sizeof(unsigned long long), c->stream));
+  GM_CUDA(cudaMemsetAsync(c->async_flag.p, 0, 4 * sizeof(uint32_t), c->stream));
+  GM_CUDA(cudaStreamSynchronize(c->stream));
+  const uint32_t n_async = c->async_open;
+  c->async_open = 0;
+  const bool redo = c->h_async[0] != 0 || c->h_async[1] != 0;
+  if (redo) {
+    // some chunk needed a host decision: the whole batch again, synchronously, from empty lists
+    const std::vector<uint32_t> chunks = c->chunks_since_upload;
+    if (int r = gm_results_clear(c)) return r;
+    c->pending = false;
+    c->chunks_since_upload.clear();
+    for (uint32_t id : chunks)
+      if (int r = gm_align_chunk(c, id, stats)) return r;
+    const bool dl = c->dl_open;
+    c->traced_async = c->dl_open = false;
+    if (dl) return gm_results_download(c, c->dl_hits, c->dl_counts);   // the enqueued copy carried the wrong lists
+    return 0;
+  }
+  {
+    const bool traced = c->traced_async;
+    c->traced_async = c->dl_open = false;
+    if (traced && c->h_async[13])
+      return fail(GM_ERR_ARGUMENT, "%u hits cannot be traced back: their db chunk is not resident in this "
+                  "context", c->h_async[13]);
+    if (traced && stats) {
+      stats->tracebacks += c->h_async[12];
+      stats->kernel_launches += 2;
+    }
+  }
+  if (stats) {
+    unsigned long long ctr[4];
+    memcpy(ctr, c->h_async + 4, sizeof(ctr));
+    stats->cells += ctr[0];
+    stats->seed_positions += ctr[1];
+    stats->candidates += ctr[2];
+    stats->candidate_chunks += n_async;
+    stats->kernel_launches += n_async * 7;   // search, check, scan, SW, cells, merge, flag
+    for (uint32_t k = 0; k < n_async; ++k) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->async_ev[k * 4 + 0], c->async_ev[k * 4 + 1]);
+      stats->ms_search += ms;
+      cudaEventElapsedTime(&ms, c->async_ev[k * 4 + 1], c->async_ev[k * 4 + 2]);
+      stats->ms_score += ms;
+      cudaEventElapsedTime(&ms, c->async_ev[k * 4 + 2], c->async_ev[k * 4 + 3]);
+      stats->ms_merge += ms;
+    }
+  }
+  return 0;
+}
+
+// gm_query_upload / gm_results_download without the trailing synchronisation: the copies are
+// enqueued (host buffers should be pinned to overlap), completion is gm_wait.  The download first
+// runs the deferred TraceBack of the survivors.
+extern "C" int gm_query_upload_async(gm_context *c, const uint8_t *seqs, uint32_t n, uint32_t L,
+                                     const uint8_t *name_break) {
+  if (c && c->async_open)
+    if (int r = gm_wait(c, nullptr)) return r;   // a new batch replaces the lists the old one still merges into
+  c->no_sync_upload = true;
+  const int r = gm_query_upload(c, seqs, n, L, name_break);
+  c->no_sync_upload = false;
+  return r;
+}
+
+extern "C" int gm_results_download_async(gm_context *c, gm_hit *hits, uint32_t *counts) {
+  if (int r = check_ctx(c)) return r;
+  if (int r = ensure_query_state(c)) return r;
+  if (int r = async_state(c)) return r;
+  c->no_sync_download = true;
+  const int r = gm_results_download(c, hits, counts);
+  c->no_sync_download = false;
+  c->dl_hits = hits;
+  c->dl_counts = counts;
+  c->dl_open = r == 0;
+  return r;
 }
 
 int trace_before_slot_change(gm_context *c, uint32_t id) {
@@ -1236,7 +1483,7 @@ extern "C" int gm_results_download(gm_context *c, gm_hit *hits, uint32_t *counts
   if (counts)
     GM_CUDA(cudaMemcpyAsync(counts, c->hit_cnt[c->cur_hits].p, (size_t)c->n_queries * 4,
                             cudaMemcpyDeviceToHost, c->stream));
-  GM_CUDA(cudaStreamSynchronize(c->stream));
+  if (!c->no_sync_download) GM_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <condition_variable>
 #include <fstream>
 #include <iostream>
@@ -484,7 +485,18 @@ int run_aln(int argc, char **argv) {
         shards[0].capacity = capacity;
         check(gm_set_candidate_capacity(ctx, capacity), "gm_set_candidate_capacity");
         check(gm_query_upload(ctx, q.seqs.data(), q.n, q.length, name_break.data()), "gm_query_upload");
-        for (uint32_t c = 0; c < n_chunks; ++c) {
+        bool done = false;
+        if (!o.verbose && std::find(resident.begin(), resident.end(), (char)0) == resident.end()) {
+          // everything resident and no per-chunk report wanted: the whole batch is enqueued without a
+          // host round trip (gm_align_chunk_async); gm_wait redoes it synchronously by itself when a
+          // chunk needed a host decision.  A buffer limit sends us to the loop below, which grows it.
+          for (uint32_t c = 0; c < n_chunks; ++c) check(gm_align_chunk_async(ctx, c), "gm_align_chunk_async");
+          const int rc = gm_wait(ctx, nullptr);
+          if (rc == 0) done = true;
+          else if (rc != GM_ERR_CAPACITY) check(rc, "gm_wait");
+          else check(gm_query_upload(ctx, q.seqs.data(), q.n, q.length, name_break.data()), "gm_query_upload");
+        }
+        for (uint32_t c = 0; c < n_chunks && !done; ++c) {
           if (!resident[c]) {     // streamed chunk: like the reference, read and uploaded per query chunk
             DbChunk full;
             if (!read_db_chunk(o.db, (int)c, &full, true)) throw std::runtime_error("db chunk file vanished");

@@ -169,6 +169,23 @@ int gm_query_upload(gm_context *ctx, const uint8_t *seqs, uint32_t n_queries, ui
  * Chunks must be presented in ascending db order (Merge carries state, aligner.cpp:114-174). */
 int gm_align_chunk(gm_context *ctx, uint32_t chunk_id, gm_stats *stats);
 
+/* Asynchronous layer: the same work enqueued on the context's stream, completion = gm_wait.
+ *   gm_query_upload_async      H2D of a query chunk (pin the host buffer to overlap; keep it alive
+ *                              until gm_wait); waits for a previous batch that is still open
+ *   gm_align_chunk_async       seed search + SW extension + Merge of one db chunk, no host round trip:
+ *                              the decisions the host takes from the per-query counts (candidate budget
+ *                              -l, buffer limits; aligner.cpp:511-516) are recorded on the device
+ *   gm_results_download_async  deferred TraceBack of the survivors + D2H of the hit lists
+ *   gm_wait                    synchronises; if any enqueued chunk needed a host decision the whole
+ *                              batch is redone through the synchronous calls (identical results) and an
+ *                              enqueued download is repeated; fills stats (may be NULL)
+ * Chunks must still be presented in ascending db order. */
+int gm_query_upload_async(gm_context *ctx, const uint8_t *seqs, uint32_t n_queries, uint32_t query_len,
+                          const uint8_t *name_break);
+int gm_align_chunk_async(gm_context *ctx, uint32_t chunk_id);
+int gm_results_download_async(gm_context *ctx, gm_hit *hits, uint32_t *counts);
+int gm_wait(gm_context *ctx, gm_stats *stats);
+
 /* gm_align_chunk in two halves, for pipelines that receive the carried hit lists from another
  * GPU while this one is already searching: prepare = seed search + SW extension of every
  * candidate chunk (independent of the hit lists), merge = the Merge (+TraceBack) calls. */

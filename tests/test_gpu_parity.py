@@ -207,3 +207,38 @@ def test_candidates_transfer_between_contexts(name, world):
             assert ok, (name, r, i, field)
         ctx.close()
     front_ctx.close()
+
+
+@pytest.mark.parametrize("name", WORKLOADS)
+def test_async_layer_matches_the_oracle(gpu_ctx, name):
+    """gm_query_upload_async / gm_align_chunk_async / gm_results_download_async / gm_wait: the whole
+    batch enqueued without a host round trip.  "repeats" (candidate budget 3000: the chunk rule cuts)
+    trips the device-side flag and is redone synchronously inside gm_wait; "options" (best 24, -t 3)
+    is not eligible and runs synchronously inside the async call; the others stay asynchronous.
+    Every variant must give the oracle's hit lists."""
+    import torch
+    db, qchunks, kw = H.workload(name)
+    opt = O.Options(**kw)
+    H.setup_context(gpu_ctx, db, opt)
+    for qc in qchunks:
+        ref = O.align_chunk(qc, db, opt)
+        q = torch.from_numpy(np.ascontiguousarray(qc.seqs)).pin_memory()
+        nb = torch.from_numpy(np.ascontiguousarray(qc.name_breaks().astype(np.uint8))).pin_memory()
+        hits_t = torch.zeros((qc.n * gpu_ctx.cap * 9,), dtype=torch.int32).pin_memory()
+        counts_t = torch.zeros((qc.n,), dtype=torch.int32).pin_memory()
+        for rep in range(2):      # twice: the second batch starts while nothing was waited for explicitly
+            gpu_ctx.query_upload_async_ptr(q.data_ptr(), qc.n, qc.seqs.shape[1], nb.data_ptr())
+            for ci in range(len(db.chunks)):
+                gpu_ctx.align_chunk_async(ci)
+            gpu_ctx.results_download_async_ptr(hits_t.data_ptr(), counts_t.data_ptr())
+        st = capi.GmStats()
+        gpu_ctx.wait(st)
+        counts = counts_t.numpy().view(np.uint32)
+        hits = hits_t.numpy().view(capi.HIT_DTYPE).reshape(qc.n, gpu_ctx.cap)
+        assert np.array_equal(counts, ref.counts), name
+        for i in range(qc.n):
+            ok, field = H.hits_equal(hits[i, :counts[i]], ref.hits[i, :counts[i]])
+            assert ok, (name, i, field)
+        if name != "options":      # the synchronous stand-in inside the async call reports no stats
+            assert st.cells > 0 and st.candidates > 0
+    assert int(ref.counts.sum()) > 0
