@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--db-residues", type=float, default=1e9)
     ap.add_argument("--chunk-mib", type=float, default=120.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample-mib", type=float, default=32.0, help="--impl reference: db sample per step")
+    ap.add_argument("--ref-queries-per-core", type=int, default=256)
     ap.add_argument("--no-extra", action="store_true", help="skip the config 4 / config 5 blocks")
     ap.add_argument("--extra-steps", type=int, default=2)
     ap.add_argument("--c4-queries", type=int, default=64, help="config 4: queries per step (sample of the 10 k)")
@@ -357,6 +359,24 @@ def rooflines(spec, st, n_launch_front, dpx_rate):
              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"})
 
 
+def config_dict(spec, world):
+    """The workload description both arms print (the reference arm times a bounded sample of it)."""
+    sharded = world > 1
+    return {
+        "workload": spec.workload, "queries_per_step": spec.queries, "query_len": spec.length,
+        "db_chunks": len(spec.chunk_bytes), "db_bytes": int(sum(spec.chunk_bytes)),
+        "max_list_length": spec.max_list_length,
+        "parallelism": (f"db chunks (index) sharded over {world} rank(s) for search + SW; candidates "
+                        "all-to-all by query slice over NCCL; Merge + TraceBack per query slice"
+                        if sharded else "1 rank: front context (search + SW) and back context (Merge + "
+                        "TraceBack) on one GPU, all db chunks resident"),
+        "pipeline": "back stage of batch s overlaps the front stage of batch s+1 (own stream, own host thread)",
+        "cache": "inputs larger than L2: every step streams the index positions and windows of all db "
+                 "chunks from HBM",
+        "traceback": "deferred to survivors",
+    }
+
+
 def result_block(spec, arm, steps, warmup, dpx_rate, with_clocks=True):
     """Device-resident and e2e timing of one workload + checksum -> dict (valid on rank 0)."""
     (dev_ms, wall_ms), (cells, cands, launches, positions), st, clocks = arm.timed(steps, warmup, False)
@@ -368,19 +388,7 @@ def result_block(spec, arm, steps, warmup, dpx_rate, with_clocks=True):
     out = {
         "value": cells / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_per_step,
         "queries_per_s": spec.queries / (ms_per_step * 1e-3),
-        "config": {
-            "workload": spec.workload, "queries_per_step": spec.queries, "query_len": spec.length,
-            "db_chunks": arm.n_chunks, "db_bytes": int(sum(spec.chunk_bytes)),
-            "max_list_length": spec.max_list_length,
-            "parallelism": (f"db chunks (index) sharded over {world} rank(s) for search + SW; candidates "
-                            "all-to-all by query slice over NCCL; Merge + TraceBack per query slice"
-                            if sharded else "1 rank: front context (search + SW) and back context (Merge + "
-                            "TraceBack) on one GPU, all db chunks resident"),
-            "pipeline": "back stage of batch s overlaps the front stage of batch s+1 (own stream, own host thread)",
-            "cache": "inputs larger than L2: every step streams the index positions and windows of all db "
-                     "chunks from HBM",
-            "traceback": "deferred to survivors",
-        },
+        "config": config_dict(spec, world),
         "e2e": {"value": e_cells / (e_wall_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_wall_ms / steps,
                 "device_ms_per_step": e_dev_ms / steps,
                 "queries_per_s": spec.queries / (e_wall_ms / steps * 1e-3),
@@ -466,8 +474,10 @@ def run_ours(a):
         for spec in (c4, c5, c5l):
             try:
                 arm = Arm(spec, torch, dist, rank, world, local, matrix)
-                blk = result_block(spec, arm, a.extra_steps, 1, dpx_rate, with_clocks=False)
-                blk["steps"], blk["warmup"] = a.extra_steps, 1
+                # warm-up = one pass over every query batch: device buffers that grow with a batch's
+                # candidate count (Merge scratch) reach their steady size before the timed region
+                blk = result_block(spec, arm, a.extra_steps, spec.n_batches, dpx_rate, with_clocks=False)
+                blk["steps"], blk["warmup"] = a.extra_steps, spec.n_batches
                 if rank == 0 and world == 1 and not a.no_cpu_baseline and spec is not c5l:
                     try:
                         blk["cpu_baseline"] = cpu_baseline(spec, arm.sample, arm.q_all[0].numpy(), matrix, torch, local)
@@ -582,8 +592,8 @@ def run_reference(a):
     probe = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
     tmp = tempfile.mkdtemp(prefix="gm_ref_")
     try:
-        seq, starts = workloads.synth_chunk(1, 0, 16 << 20)
-        per_proc = 128
+        seq, starts = workloads.synth_chunk(1, 0, int(a.ref_sample_mib * (1 << 20)))
+        per_proc = a.ref_queries_per_core
         qs = workloads.synth_queries(2, seq[: 4 << 20].copy(), per_proc * cores, a.length)
         db, qcs = _write_sample(tmp, seq, starts, qs, cores)
         # cells of the sample (untimed): candidates from the reference stage probe or the oracle
@@ -647,7 +657,7 @@ def run_reference(a):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": wall / a.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s32",
             "data": "synthetic", "queries_per_s": qs.shape[0] * a.steps / wall,
-            "config": {"workload": "config3 (bounded sample): " + sample},
+            "config": config_dict(specs(a)[0], int(os.environ.get("WORLD_SIZE", 1))),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": len(qcs), "kind": kind,
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

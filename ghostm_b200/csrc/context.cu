@@ -1188,7 +1188,8 @@ int merge_impl(gm_context *c, uint32_t first, uint32_t end, gm_stats *stats, boo
   if (async) n_new = std::min<uint64_t>(c->cand_capacity, c->opt.max_list_length);   // the host never saw the counts
   else for (uint32_t q = first; q < end; ++q) n_new += c->h_counts[q];
   const uint64_t big_cap = 2 * (n_new + (uint64_t)c->n_queries * c->cap) + 2;  // records + stopper positions
-  GM_CUDA(c->big_scratch.ensure(big_cap));
+  if (big_cap > c->big_scratch.n)     // grows in steps of 1.5x: a reallocation stalls every stream of the device
+    GM_CUDA(c->big_scratch.ensure(big_cap + big_cap / 2));
   MergeParams p = {};
   p.queries = c->queries.p;
   p.query_len = c->query_len;
@@ -1217,7 +1218,7 @@ int merge_impl(gm_context *c, uint32_t first, uint32_t end, gm_stats *stats, boo
   p.jobs = c->jobs.p;
   p.n_jobs = c->small.p + 3;
   p.big_scratch = c->big_scratch.p;
-  p.big_capacity = big_cap;
+  p.big_capacity = c->big_scratch.n;
   p.big_cursor = c->counters.p + 3;
   p.error = reinterpret_cast<int *>(c->small.p + 4);
   p.run_counter = c->small.p + 5;

@@ -66,6 +66,31 @@ def main():
                     ok, field = H.hits_equal(got, ref.hits[i, :ref.counts[i]])
                     assert ok, (name, rank, i, field)
                 n_hits += int(counts.sum())
+            # the same query chunk twice through the pipelined driver bench.py uses (back stage on its
+            # own thread, overlapped with the next batch's front stage; host buffers in, host buffers out)
+            n_slice = stop - base
+            q_pin = torch.from_numpy(np.ascontiguousarray(qc.seqs)).pin_memory()
+            nb_pin = torch.from_numpy(np.ascontiguousarray(qc.name_breaks().astype(np.uint8))).pin_memory()
+            hits_pin = torch.zeros((max(n_slice, 1) * back_ctx.cap * 9,), dtype=torch.int32).pin_memory()
+            counts_pin = torch.zeros((max(n_slice, 1),), dtype=torch.int32).pin_memory()
+            pipe = shard.GpuPipeline(front_ctx, back_ctx, qc.n, qc.seqs.shape[1], 1 << 22, f"cuda:{local}", dist,
+                                     rank, world, n_chunks, bounds)
+            for _ in range(2):
+                pipe.submit(queries_ptr=q_pin.data_ptr(), slice_ptr=q_pin[base:stop].data_ptr() if n_slice else 0,
+                            name_break_ptr=nb_pin.data_ptr(),
+                            slice_break_ptr=nb_pin[base:stop].data_ptr() if n_slice else 0,
+                            hits_ptr=hits_pin.data_ptr(), counts_ptr=counts_pin.data_ptr())
+            pipe.drain()
+            pipe.close()
+            if n_slice:
+                got_c = counts_pin.numpy().view(np.uint32)[:n_slice]
+                got_h = hits_pin.numpy().view(capi.HIT_DTYPE)[: n_slice * back_ctx.cap].reshape(n_slice, back_ctx.cap)
+                assert np.array_equal(got_c, ref.counts[base:stop]), (name, rank, "pipelined")
+                for i in range(base, stop):
+                    got = got_h[i - base, :got_c[i - base]].copy()
+                    got["query_id"] += base
+                    ok, field = H.hits_equal(got, ref.hits[i, :ref.counts[i]])
+                    assert ok, (name, rank, i, field, "pipelined")
         front_ctx.close()
         back_ctx.close()
         print(f"SHARD_GPU_OK {name} rank {rank}/{world} hits {n_hits}", flush=True)
