@@ -406,6 +406,7 @@ def result_block(spec, arm, steps, warmup, dpx_rate, with_clocks=True):
         "e2e_host_ms_per_step_rank0": e_st.get("host_ms_per_step"),
         "e2e_stage_ms_per_step_rank0": {k: e_st[k] / steps for k in ("ms_search", "ms_score", "ms_merge", "ms_traceback")},
         "candidates_per_step": cands / steps, "cells_per_step": cells / steps,
+        "seed_positions_per_step": positions / steps,
         "setup_s": arm.setup_s,
     }
     if with_clocks:
