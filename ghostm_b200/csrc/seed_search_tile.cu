@@ -57,6 +57,7 @@ constexpr uint32_t kTlMagic31 = 138547333u;  // ceil(2^32 / 31): x / 31 == umulh
 struct TileShared {
   uint32_t lbeg[kTlLists];               // first usable entry of list j (aligner.cpp:430-431)
   uint32_t query, stage_n;
+  uint32_t dummy[32];                    // per-lane target of the atomics of lanes that carry no mark
   unsigned long long base;
   unsigned long long visited;
 };
@@ -74,14 +75,10 @@ __device__ __forceinline__ uint32_t tl_smem_addr(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-// old = atomicOr on a shared-memory word when `on`, else 0.
-__device__ __forceinline__ uint32_t tl_atoms_or(uint32_t addr, uint32_t v, bool on) {
-  uint32_t old = 0;
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q atom.shared.or.b32 %0, [%1], %2;\n\t}"
-      : "+r"(old)
-      : "r"(addr), "r"(v), "r"((uint32_t)on)
-      : "memory");
+// atomicOr on a shared-memory word given by its shared-window address
+__device__ __forceinline__ uint32_t atomicOr_shared(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
   return old;
 }
 
@@ -134,6 +131,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) seed_search_tile_kernel(const S
   uint32_t *emap = p.tl_emap + (size_t)blockIdx.x * p.tl_emap_stride;   // absolute emit words, all zero
   uint32_t occ_s = tl_smem_addr(occ);
   asm volatile("mov.u32 %0, %0;" : "+r"(occ_s));   // keep the window address in a register
+  const uint32_t dummy_s = tl_smem_addr(&sh.dummy[lane]);
   const uint32_t *__restrict__ positions = p.positions;
 
   for (uint32_t i = tid; i < p.tl_ring; i += kThreads) sring[i] = 0;
@@ -299,13 +297,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) seed_search_tile_kernel(const S
             const uint2 cc = *reinterpret_cast<const uint2 *>(&wt[i].z);
             return (pv - (lane == 0 ? cc.y : cc.x)) >> r;
           };
+          // Both atomics are unconditional: a lane without a mark ORs 0 into its own dummy word (32
+          // words, 32 banks).  No divergence between the steps of a batch, so their shuffle -> atomic
+          // chains overlap.
           auto arrive = [&](uint32_t l, uint32_t &old, uint32_t &old2) {
             const uint32_t lp = __shfl_up_sync(kFull, l, 1);   // lane 0 receives its own l: never a mark
             const bool mark = l != lp;
             const uint32_t qw = tl_div31(l), b = l - qw * 31u;
             const uint32_t wa = occ_s + 4u * qw;
-            old = tl_atoms_or(wa, 1u << b, mark);
-            old2 = tl_atoms_or(wa - 4u, 0x80000000u, mark && b == 0);
+            const bool low = mark && b == 0;
+            old = atomicOr_shared(mark ? wa : dummy_s, mark ? 1u << b : 0u);
+            old2 = atomicOr_shared(low ? wa - 4u : dummy_s, low ? 0x80000000u : 0u);
+            if (!mark) old = 0;
+            if (!low) old2 = 0;
           };
           // a full batch: regions, then all atomics back to back, then the (rare) events
           auto process = [&](uint32_t i, const uint32_t (&pv)[kTlUnroll]) {
