@@ -22,7 +22,7 @@ def dram_bytes(path):
 
 
 sw_csv, se_csv, bench_json, label = sys.argv[1:5]
-b = json.loads(open(bench_json).read().strip().split("\n")[-1])
+b = json.loads([ln for ln in open(bench_json).read().split("\n") if ln.startswith("{")][-1])
 cfg = b["config"]
 share = (120 << 20) / cfg["db_bytes"]          # chunk 0 of 8: a full 120 MiB chunk
 sw_bytes, sw_name, sw_ms = dram_bytes(sw_csv)
