@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--ref-queries-per-core", type=int, default=256)
     ap.add_argument("--no-extra", action="store_true", help="skip the config 4 / config 5 blocks")
     ap.add_argument("--extra-steps", type=int, default=2)
+    ap.add_argument("--extra-max-gpus", type=int, default=2)
     ap.add_argument("--c4-queries", type=int, default=64, help="config 4: queries per step (sample of the 10 k)")
     ap.add_argument("--c5-queries", type=int, default=10000)
     ap.add_argument("--cpu-sample-mib", type=float, default=32.0)
@@ -471,7 +472,10 @@ def run_ours(a):
     del arm
 
     extra = {}
-    if not a.no_extra:
+    # config 4 has two db chunks and config 5 one: beyond two ranks there is nothing left to shard
+    if not a.no_extra and world > a.extra_max_gpus:
+        extra = {"skipped": f"config 4 / config 5 blocks run at N <= {a.extra_max_gpus} (2 and 1 db chunks)"}
+    elif not a.no_extra:
         for spec in (c4, c5, c5l):
             try:
                 arm = Arm(spec, torch, dist, rank, world, local, matrix)
