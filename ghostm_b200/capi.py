@@ -13,7 +13,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libghostm_b200.so")
+LIB_PATH = os.environ.get("GHOSTM_B200_LIB") or os.path.join(_HERE, "libghostm_b200.so")   # override: A/B builds
 
 DEFAULT_SEARCH_VARIANT = 4
 

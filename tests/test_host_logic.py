@@ -296,3 +296,42 @@ def test_parallel_partition_identity():
             m = x if gt(x, z) else (z if gt(y, z) else y)
         a[f], a[m] = a[m], a[f]
         assert sequential(a, f, l) == parallel(a, f, l)
+
+
+def test_hit_checksum_is_slice_invariant_and_order_sensitive():
+    """bench.py's per-N proof: the checksum of a batch's hit lists summed over query slices does not
+    depend on where the slices are cut, and changes when two hits of a list swap places."""
+    rng = np.random.default_rng(5)
+    n, cap = 97, 10
+    hits = rng.integers(0, 2 ** 32, size=(n, cap, 9), dtype=np.uint64).astype(np.uint32)
+    counts = rng.integers(0, cap + 1, size=n).astype(np.uint32)
+    full = shard.hit_checksum(hits, counts, 0)
+    for cuts in ([40], [1, 2, 96], [13, 50, 51, 80]):
+        b = [0] + cuts + [n]
+        parts = sum(shard.hit_checksum(hits[b[i]:b[i + 1]], counts[b[i]:b[i + 1]], b[i]) for i in range(len(b) - 1))
+        assert parts & (2 ** 64 - 1) == full
+    q = int(np.flatnonzero(counts >= 2)[0])
+    swapped = hits.copy()
+    swapped[q, 0], swapped[q, 1] = hits[q, 1].copy(), hits[q, 0].copy()
+    assert shard.hit_checksum(swapped, counts, 0) != full
+    beyond = hits.copy()
+    beyond[q, counts[q]:] += 1          # records past the count are not part of the list
+    assert shard.hit_checksum(beyond, counts, 0) == full
+
+
+def test_back_worker_runs_in_order_and_surfaces_errors():
+    w = shard.BackWorker()
+    seen = []
+    tickets = [w.submit(lambda i=i: seen.append(i)) for i in range(50)]
+    w.drain()
+    assert seen == list(range(50)) and all(t.is_set() for t in tickets)
+
+    def boom():
+        raise ValueError("back stage failed")
+    t = w.submit(boom)
+    later = w.submit(lambda: seen.append("skipped"))
+    t.wait(); later.wait()
+    with pytest.raises(ValueError):
+        w.drain()
+    assert "skipped" not in seen        # jobs behind a failure do not run
+    w.close()
