@@ -572,6 +572,10 @@ bool search_tile_geometry(uint32_t threshold, uint32_t list_len, uint32_t shift,
   budget -= 1024 + 1024;
   uint32_t nw = (uint32_t)((budget / 4) & ~(size_t)127);
   if (nw > ((words_needed + 127u) & ~127u)) nw = (words_needed + 127u) & ~127u;
+  if (const char *env = getenv("GM_TILE_NW")) {   // tests: small tiles, so that small inputs span many of them
+    const uint32_t cap = ((uint32_t)atoi(env) + 127u) & ~127u;
+    if (cap >= 256 && cap < nw) nw = cap;
+  }
   TileGeometry best = {};
   for (; nw >= 256; nw -= 128) {
     const unsigned long long tile_pos = ((unsigned long long)31 * nw) << log_region;

@@ -128,3 +128,31 @@ def test_query_lengths_across_the_traceback_kernels(gpu_ctx, length):
     db = formats.make_db(dbs, dbn, 4, 1)
     qc = formats.make_query_chunks(qs, qn, length, 128)[0]
     assert _check(gpu_ctx, db, qc, O.Options()) > 0
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(shift=1), dict(shift=5, log_region=2), dict(log_region=7),
+                                dict(log_region=1, shift=3)])
+@pytest.mark.parametrize("nw", [256, 640])
+def test_tile_search_many_tiles_and_carry_zones(gpu_ctx, kw, nw, monkeypatch):
+    """The tile seed-search kernel with its bitmap capped to a few hundred words (GM_TILE_NW), so a
+    1 M-residue chunk spans dozens of tiles: slices, carry zones between tiles (their width depends
+    on shift and region size), the split table and the scanner's range cuts all get exercised with
+    non-default geometry.  Candidates must equal the oracle's, query by query."""
+    monkeypatch.setenv("GM_TILE_NW", str(nw))
+    dbs, dbn = synth.protein_db(91, 1_000_000)
+    qs, qn = synth.queries_from_db(92, dbs, 96, 75, min_length=20)
+    db = formats.make_db(dbs, dbn, 4, 1)
+    qc = formats.make_query_chunks(qs, qn, 75, 128)[0]
+    opt = O.Options(**kw)
+    H.setup_context(gpu_ctx, db, opt)
+    gpu_ctx.query_upload(qc.seqs, qc.name_breaks())
+    total_ref = 0
+    for ci, chunk in enumerate(db.chunks):
+        counts, total = gpu_ctx.search(ci)
+        ids, cand = gpu_ctx.candidates(0, qc.n, total)
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        for q in range(qc.n):
+            ref = O.search_query(qc.seqs[q], chunk, opt)
+            assert np.array_equal(ref, cand[off[q]:off[q + 1]]), (kw, nw, ci, q)
+            total_ref += ref.shape[0]
+    assert total_ref > 0
