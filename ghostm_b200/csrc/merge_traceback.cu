@@ -17,6 +17,8 @@
 // the forward end over at most L + 2*extend*2*2^r columns, stop at the first SEQUENCE_END,
 // track match count and alignment length along the argmax path (diagonal first, then strictly
 // greater insertion, then strictly greater deletion), keep the FIRST strict maximum.
+#include <stdlib.h>
+
 #include "gm_common.cuh"
 
 namespace gm {
@@ -665,6 +667,126 @@ __global__ void __launch_bounds__(256) traceback_warp_kernel(const TracebackPara
   }
 }
 
+// Group TraceBack for short queries (L <= G * RL <= 80): the systolic wavefront of
+// traceback_warp_kernel on G lanes per hit instead of 32, so a warp traces 32 / G hits at once and
+// no lane idles (at L = 75 the full-warp kernel keeps 19 of 32 lanes busy).  Against one thread per
+// hit (traceback_reg_kernel: 150 state registers, 8 warps per SM, one long dependent chain) a lane
+// holds RL = ceil(L / G) rows, so ~3x the warps are resident and G chains run per hit.
+template <int G, int RL>
+__global__ void __launch_bounds__(256) traceback_group_kernel(const TracebackParams p) {
+  __shared__ int16_t mat[kAlphabet * kAlphabet];
+  for (int i = threadIdx.x; i < kAlphabet * kAlphabet; i += blockDim.x) mat[i] = (int16_t)p.matrix[i];
+  __syncthreads();
+  constexpr uint32_t kGroups = 32 / G;
+  const uint32_t n_jobs = *p.n_jobs;
+  const uint32_t lane = threadIdx.x & 31, gl = lane % G, grp = lane / G;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int L = (int)p.query_len;
+  const int go = p.open_gap, ge = p.extend_gap;
+  for (uint32_t job0 = gwarp * kGroups; job0 < n_jobs; job0 += n_warps * kGroups) {
+    const uint32_t job = job0 + grp;
+    const bool have = job < n_jobs;
+    gm_hit h = {};
+    ChunkRef chunk = {nullptr, nullptr};
+    const uint8_t *query = p.queries;
+    uint32_t db_offset = 0, len = 0;
+    if (have) {
+      h = p.hits[p.jobs[job]];
+      chunk = p.chunks[h.db_chunk];
+      query = p.queries + (size_t)h.query_id * L;
+      db_offset = h.db_end;
+      len = p.base_len;
+      if (db_offset < len) len = db_offset + 1;                       // aligner.cpp:802-805
+    }
+    uint32_t qk[RL], he[RL], pay[RL];
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+      const int i = (int)gl * RL + r;
+      qk[r] = (have && i < L) ? query[L - 1 - i] : 0xFFu;             // 0xFF: no such row
+      he[r] = 0;
+      pay[r] = 0;
+    }
+    int best = 0;
+    uint32_t best_j = 0, best_i = 0, best_pay = 0;
+    int out_h = 0, out_del = 0, diag_h = 0;       // last row of this lane / boundary of the previous column
+    uint32_t out_pay = 0, diag_pay = 0;
+    uint32_t cbuf = kSeqEnd, c_cur = kSeqEnd;
+    bool stopped = false;
+    const uint32_t steps = __reduce_max_sync(kFull, len) + G - 1;      // the longest window of the warp's hits
+    for (uint32_t t = 0; t < steps; ++t) {
+      if ((t % G) == 0) {                                             // next G columns, one per lane of the group
+        const uint32_t idx = t + gl;
+        cbuf = idx < len ? chunk.seq[db_offset - idx] : (uint32_t)kSeqEnd;
+      }
+      const uint32_t c0 = __shfl_sync(kFull, cbuf, t % G, G);
+      c_cur = __shfl_up_sync(kFull, c_cur, 1, G);
+      if (gl == 0) c_cur = c0;
+      int in_h = __shfl_up_sync(kFull, out_h, 1, G), in_del = __shfl_up_sync(kFull, out_del, 1, G);
+      uint32_t in_pay = __shfl_up_sync(kFull, out_pay, 1, G);
+      if (gl == 0) { in_h = 0; in_del = 0; in_pay = 0; }              // below row L-1: zeros (:791-797)
+      const uint32_t j = t - gl;
+      bool active = t >= gl && j < len && !stopped;
+      if (active && c_cur == kSeqEnd) { stopped = true; active = false; }   // aligner.cpp:927-929
+      if (active) {
+        const uint32_t c = c_cur;
+        const int16_t *row = mat + c * kAlphabet;
+        int temp_score = diag_h, below_h = in_h, del = in_del;
+        uint32_t temp_pay = diag_pay, below_pay = in_pay;
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          if (qk[r] != 0xFFu) {
+            const uint32_t old = he[r], old_pay = pay[r];
+            const int old_h = (int)old >> 16;
+            int ins = (int)(int16_t)(old & 0xFFFFu);
+            const int s = temp_score + row[qk[r]];
+            int local = 0;
+            uint32_t np = 0;
+            if (s > 0) { local = s; np = temp_pay + (c == qk[r] ? 0x10001u : 0x1u); }
+            ins = max(ins + ge, old_h + go);
+            if (ins > local) { local = ins; np = old_pay + 1; }
+            del = max(del + ge, below_h + go);
+            if (del > local) { local = del; np = below_pay + 1; }
+            temp_score = old_h;
+            temp_pay = old_pay;
+            he[r] = ((uint32_t)local << 16) | ((uint32_t)ins & 0xFFFFu);
+            pay[r] = np;
+            below_h = local;
+            below_pay = np;
+            if (local > best) { best = local; best_j = j; best_i = gl * RL + r; best_pay = np; }  // first max
+          }
+        }
+        out_h = below_h;
+        out_pay = below_pay;
+        out_del = del;
+      }
+      diag_h = in_h;          // boundary of column j becomes the diagonal of column j+1
+      diag_pay = in_pay;
+    }
+    // largest score; among equals the earliest cell in scan order (column, then row)
+    unsigned long long key = ((unsigned long long)(uint32_t)best << 32) |
+                             (0xFFFFFFFFu - ((best_j << 11) | best_i));
+    uint32_t bp = best_pay;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const unsigned long long k2 = __shfl_xor_sync(kFull, key, o, G);
+      const uint32_t p2 = __shfl_xor_sync(kFull, bp, o, G);
+      if (k2 > key) { key = k2; bp = p2; }
+    }
+    if (gl == 0 && have) {
+      const uint32_t max_start = (0xFFFFFFFFu - (uint32_t)key) >> 11;
+      const uint32_t seq_pos = chunk.seq_starts[h.db_id];
+      const uint32_t max_match = bp >> 16, max_len = bp & 0xFFFFu;
+      h.db_start = db_offset - max_start - seq_pos;                   // aligner.cpp:941, :715
+      h.db_end = db_offset - seq_pos;                                 // :716
+      h.seq_id = (float)max_match / (float)(int)max_len;              // :945
+      h.aln_len = max_len;
+      h.aln_match = max_match;
+      p.hits[p.jobs[job]] = h;
+    }
+    __syncwarp();
+  }
+}
+
 // Collect the result slots whose TraceBack is pending and whose db chunk is resident here.
 __global__ void collect_pending_kernel(const gm_hit *hits, const uint32_t *counts, uint32_t n_queries,
                                        uint32_t cap, const ChunkRef *chunks, uint32_t *jobs,
@@ -728,6 +850,22 @@ cudaError_t traceback_launch(const TracebackParams &p, int sm_count, cudaStream_
     return cudaGetLastError();
   }
   if (fast && traceback_fast_ok(p.query_len, p.open_gap, p.extend_gap)) {
+    static const int group = [] { const char *e = getenv("GM_TB_GROUP"); return e ? atoi(e) : 4; }();
+    if (group == 4) {       // 4 lanes per hit (8 hits per warp)
+      const int grid = sm_count * 8;
+      if (p.query_len <= 40) traceback_group_kernel<4, 10><<<grid, 256, 0, stream>>>(p);
+      else if (p.query_len <= 64) traceback_group_kernel<4, 16><<<grid, 256, 0, stream>>>(p);
+      else if (p.query_len <= 76) traceback_group_kernel<4, 19><<<grid, 256, 0, stream>>>(p);
+      else traceback_group_kernel<4, 20><<<grid, 256, 0, stream>>>(p);
+      return cudaGetLastError();
+    }
+    if (group == 8) {       // 8 lanes per hit (4 hits per warp)
+      const int grid = sm_count * 8;
+      if (p.query_len <= 40) traceback_group_kernel<8, 5><<<grid, 256, 0, stream>>>(p);
+      else if (p.query_len <= 64) traceback_group_kernel<8, 8><<<grid, 256, 0, stream>>>(p);
+      else traceback_group_kernel<8, 10><<<grid, 256, 0, stream>>>(p);
+      return cudaGetLastError();
+    }
     const int grid = sm_count * 2;
     if (p.query_len <= 32) traceback_reg_kernel<32><<<grid, 128, 0, stream>>>(p);
     else if (p.query_len <= 64) traceback_reg_kernel<64><<<grid, 128, 0, stream>>>(p);
