@@ -338,7 +338,7 @@ def rooflines(spec, st, n_launch_front, dpx_rate):
     peak = dpx_rate * DPX_OPS_PER_LANE_INSTR / 1e12
     # 8 B of keys_count + 4 B of key per query k-mer, 4 B per index position, 4 B per candidate
     search_bytes = st["seed_positions"] * 4 + spec.queries * n_launch_front * spec.list_len * 12 + st["candidates"] * 4
-    cand_per_launch = st["candidates"] / max(st["candidate_chunks"], 1)
+    cand_per_launch = st["candidates"] / max(n_launch_front, 1)     # per db chunk pass (one SW launch per candidate chunk)
     traffic = _measured_traffic()
     sw_t, se_t = traffic.get(spec.name + ":sw_extend"), traffic.get(spec.name + ":seed_search")
     window = spec.length + 2 * 2 + 2 * 16

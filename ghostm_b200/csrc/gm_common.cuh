@@ -15,6 +15,20 @@ constexpr uint8_t kSeqEnd = 25;   // common.h:34
 constexpr uint8_t kBaseX = 23;    // common.h:35
 constexpr uint32_t kNoId = 0xFFFFFFFFu;
 
+// Opt-in dynamic shared memory of a kernel: always raised to the device maximum (minus the kernel's
+// static part), never to the size of one launch - several contexts launch the same kernels from
+// different host threads with different sizes, and a per-launch value would race.
+template <typename K>
+inline cudaError_t allow_max_dynamic_smem(K kern) {
+  cudaFuncAttributes attr;
+  cudaError_t err = cudaFuncGetAttributes(&attr, kern);
+  if (err != cudaSuccess) return err;
+  int dev = 0, optin = 0;
+  if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+  if ((err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)attr.sharedSizeBytes);
+}
+
 // ---- SW extension ---------------------------------------------------------------------
 constexpr int kSwThreads = 256;          // 8 warps per CTA, one CTA per SM (register bound)
 constexpr int kSwWarps = kSwThreads / 32;

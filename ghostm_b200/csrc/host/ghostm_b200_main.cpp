@@ -337,7 +337,7 @@ void on_every_device(std::vector<Shard> &shards, F body) {
     });
   for (auto &w : workers) w.join();
   for (auto &sh : shards)
-    if (!sh.error.empty()) throw std::runtime_error(sh.error);
+    if (!sh.error.empty()) throw DeviceError(sh.error);   // a worker died on a gm_* call
 }
 
 // ---- output (aligner.cpp:951-1012) -------------------------------------------------------------

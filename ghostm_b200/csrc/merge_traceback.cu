@@ -819,8 +819,7 @@ size_t merge_smem_bytes(uint32_t elems_per_warp) { return (size_t)kMergeWarps * 
 
 cudaError_t merge_launch(const MergeParams &p, int sm_count, cudaStream_t stream) {
   const size_t smem = merge_smem_bytes(p.smem_elems);
-  cudaError_t err =
-      cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = allow_max_dynamic_smem(merge_kernel);
   if (err != cudaSuccess) return err;
   merge_kernel<<<sm_count, kMergeThreads, smem, stream>>>(p);   // 192 KB of lists: one CTA per SM
   return cudaGetLastError();

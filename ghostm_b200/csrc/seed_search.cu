@@ -1281,13 +1281,11 @@ cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t str
 #define GM_LAUNCH_SEARCH(TT)                                                                   \
   case TT:                                                                                     \
     if (fast) {                                                                                \
-      err = cudaFuncSetAttribute(seed_search_fast_kernel<TT, TT == 2>,                         \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+      err = allow_max_dynamic_smem(seed_search_fast_kernel<TT, TT == 2>);                      \
       if (err != cudaSuccess) return err;                                                      \
       seed_search_fast_kernel<TT, TT == 2><<<grid * 2, kFastThreads, smem, stream>>>(p);       \
     } else {                                                                                   \
-      err = cudaFuncSetAttribute(seed_search_kernel<TT>,                                       \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+      err = allow_max_dynamic_smem(seed_search_kernel<TT>);                                    \
       if (err != cudaSuccess) return err;                                                      \
       seed_search_kernel<TT><<<grid, kSearchThreads, smem, stream>>>(p);                       \
     }                                                                                          \
@@ -1299,8 +1297,7 @@ cudaError_t seed_search_launch(const SearchParams &p, int grid, cudaStream_t str
     GM_LAUNCH_SEARCH(4)
     default:   // thresholds above 4: the generic kernel with run-time plane count
       if (fast) return cudaErrorInvalidValue;
-      err = cudaFuncSetAttribute(seed_search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem);
+      err = allow_max_dynamic_smem(seed_search_kernel<0>);
       if (err != cudaSuccess) return err;
       seed_search_kernel<0><<<grid, kSearchThreads, smem, stream>>>(p);
       break;
@@ -1346,7 +1343,7 @@ template <int NW, int SLOTS, int MINB>
 static cudaError_t bucket_launch(const SearchParams &p, int sm_count, cudaStream_t stream) {
   const size_t smem = (size_t)NW * (2 * (1u << (p.tile_bits - 5)) + 1 + 64) * sizeof(uint32_t);
   auto kern = seed_search_bucket_kernel<NW, SLOTS, MINB>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = allow_max_dynamic_smem(kern);
   if (err != cudaSuccess) return err;
   int per_sm = 0;
   err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
@@ -1373,8 +1370,7 @@ bool search_hash_ok(uint32_t threshold, uint32_t list_len, uint32_t n_regions) {
 }
 
 cudaError_t seed_search_hash_launch(const SearchParams &p, int sm_count, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(seed_search_hash_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHsSmemBytes);
+  cudaError_t err = allow_max_dynamic_smem(seed_search_hash_kernel);
   if (err != cudaSuccess) return err;
   seed_search_hash_kernel<<<sm_count, kHsThreads, kHsSmemBytes, stream>>>(p);
   return cudaGetLastError();

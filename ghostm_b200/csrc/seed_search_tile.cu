@@ -537,7 +537,7 @@ size_t tile_smem_bytes(const TileGeometry &g, uint32_t list_len, int n_warps) {
 template <int NW, int MINB>
 cudaError_t tile_launch(const SearchParams &p, size_t smem, int sm_count, int max_grid, cudaStream_t stream) {
   auto kern = seed_search_tile_kernel<NW, MINB>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = allow_max_dynamic_smem(kern);
   if (err != cudaSuccess) return err;
   int per_sm = 0;
   err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);

@@ -224,8 +224,7 @@ __global__ void __launch_bounds__(128) sw_extend_s32_kernel(const SwParams p) {
 template <int R>
 cudaError_t launch_dpx(const SwParams &p, int sm_count, cudaStream_t stream) {
   const size_t smem = 2048 + (size_t)kSwWarps * R * 32 * sizeof(uint16_t);
-  cudaError_t err = cudaFuncSetAttribute(sw_extend_dpx_kernel<R>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = allow_max_dynamic_smem(sw_extend_dpx_kernel<R>);
   if (err != cudaSuccess) return err;
   sw_extend_dpx_kernel<R><<<sm_count * (R <= 40 ? 2 : 1), kSwThreads, smem, stream>>>(p);
   return cudaGetLastError();
