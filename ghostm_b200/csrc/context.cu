@@ -14,6 +14,8 @@ namespace gm {
 
 // ---- kernels defined in the other translation units -----------------------------------
 int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips);
+int sw_pair_rows(uint32_t query_len);
+cudaError_t sw_extend_pair_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream);
 cudaError_t sw_extend_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream);
 cudaError_t sw_extend_s32_launch(const SwParams &p, int sm_count, cudaStream_t stream);
 uint32_t search_tile_regions(int T, size_t smem_limit, uint32_t n_regions, bool fast);
@@ -76,7 +78,7 @@ int fail(gm_status st, const char *fmt, ...) {
 // ---- small utility kernels --------------------------------------------------------------
 
 // out[i] = exclusive prefix over i of f(in[first + i]); out[n] = total.  One CTA.
-// mode 0: f(x) = x      mode 1: f(x) = ceil(x / 64)   (SW tasks per query)
+// mode 0: f(x) = x      mode 1: f(x) = ceil(x / 64)   mode 2: f(x) = ceil(x / 32)   (SW tasks per query)
 __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *in, uint32_t first, uint32_t n,
                                                     uint32_t *out, int mode) {
   __shared__ uint32_t warp_sum[32];
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *in, uint32_t
     if (i < n) {
       v = in[first + i];
       if (mode == 1) v = (v + kSwCandPerTask - 1) / kSwCandPerTask;
+      if (mode == 2) v = (v + kSwCandPerTask / 2 - 1) / (kSwCandPerTask / 2);
     }
     uint32_t incl = v;
 #pragma unroll
@@ -1022,8 +1025,13 @@ int score_impl(gm_context *c, uint32_t first, uint32_t end, uint32_t *scores, ui
       GM_CUDA(c->strip_scratch.ensure(need));
     }
     p.strip_scratch = c->strip_scratch.p;
-    if (int r = scan_counts(c, first, end, 1, nullptr)) return r;
-    GM_CUDA(sw_extend_launch(p, rows, c->sm_count, c->stream));
+    if (const int pair_rows = sw_pair_rows(c->query_len)) {   // two lanes per candidate pair, 32 candidates per task
+      if (int r = scan_counts(c, first, end, 2, nullptr)) return r;
+      GM_CUDA(sw_extend_pair_launch(p, pair_rows, c->sm_count, c->stream));
+    } else {
+      if (int r = scan_counts(c, first, end, 1, nullptr)) return r;
+      GM_CUDA(sw_extend_launch(p, rows, c->sm_count, c->stream));
+    }
     launches = 2;
   } else {
     GM_CUDA(sw_extend_s32_launch(p, c->sm_count, c->stream));

@@ -179,6 +179,167 @@ __global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_k
   }
 }
 
+// Pair variant for queries of 41..80 residues: TWO adjacent lanes share a pair of candidates, the even
+// lane holds rows [0, RH) and the odd lane rows [RH, 2 RH) of the same DP, one column behind (a
+// two-stage systolic array): what leaves the even lane's last row at column j - H+open and the
+// vertical F - reaches the odd lane by one shuffle each and is consumed at its column j one step
+// later.  Every thread keeps RH <= 40 rows (128 registers: 4 warps per scheduler instead of 2 for a
+// full-height column), the boundary row never leaves the register file (the strip-mined kernel
+// sends it through an L2 scratch and walks the window twice), and each lane keeps its own running
+// maximum: (max, last column) of the candidate is the larger of the two, on a tie the later column.
+// One warp task = 32 candidates of one query.
+template <int RH>
+__global__ void __launch_bounds__(kSwThreads, 2) sw_extend_pair_kernel(const SwParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int16_t *matT = reinterpret_cast<int16_t *>(smem_raw);                 // [query residue][db residue]
+  uint16_t *prof_all = reinterpret_cast<uint16_t *>(smem_raw + 2048);    // per warp [2 RH][32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t odd = lane & 1;
+  uint16_t *prof = prof_all + warp * ((2 * RH + 1) * 32);
+
+  for (int i = threadIdx.x; i < kAlphabet * kAlphabet; i += blockDim.x) {
+    const int c = i >> 5, q = i & 31;  // matrix[db residue * 32 + query residue] (aligner.cpp:612-618)
+    matT[q * 32 + c] = (int16_t)p.matrix[i];
+  }
+  __syncthreads();
+
+  const int go = p.open_gap, ge = p.extend_gap;
+  const int gef = go > ge ? go : ge;  // F_{k+1} = max(F_k + max(ge,go), m_k + go), see header
+  const uint32_t go_pk = pack2(go), ge_pk = pack2(ge), gef_pk = pack2(gef);
+  const uint32_t total_tasks = p.task_prefix[p.n_q];
+  const uint32_t L = p.query_len;
+
+  while (true) {
+    uint32_t task = 0;
+    if (lane == 0) task = atomicAdd(p.task_counter, 1u);
+    task = __shfl_sync(kFull, task, 0);
+    if (task >= total_tasks) break;
+    uint32_t lo = 0, hi = p.n_q;  // task_prefix[lo] <= task < task_prefix[hi]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (p.task_prefix[mid] <= task) lo = mid; else hi = mid;
+    }
+    const uint32_t q = p.first_query + lo;
+    const uint32_t blk = task - p.task_prefix[lo];
+    const uint32_t cnt = p.cand_cnt[q], off = p.cand_off[q];
+    const uint8_t *query = p.queries + (size_t)q * L;
+
+    // the two candidates of this lane PAIR
+    const uint32_t ia = blk * 32u + (lane >> 1), ib = ia + 16;
+    uint32_t wa = 0, wb = 0, offa = 0, offb = 0;
+    if (ia < cnt) {
+      const uint32_t st = p.cand_start[off + ia];
+      offa = st >= p.extend ? st - p.extend : 0u;                       // aligner.cpp:576-579
+      wa = min(p.base_len, p.db_len - offa);                            // aligner.cpp:580-583
+    }
+    if (ib < cnt) {
+      const uint32_t st = p.cand_start[off + ib];
+      offb = st >= p.extend ? st - p.extend : 0u;
+      wb = min(p.base_len, p.db_len - offb);
+    }
+    const uint8_t *pa = p.db + offa, *pb = p.db + offb;
+    const uint32_t wmax = __reduce_max_sync(kFull, wa > wb ? wa : wb);
+
+    // per-warp query profile T[k][c] = matrix[c][query[k]] - open for the 2 RH rows.  A table row is
+    // 64 bytes = 16 banks; the odd lanes' half starts at an ODD table row, so that in every load the
+    // even lanes (row k) and the odd lanes (row k + RH) hit different halves of the 32 banks
+    constexpr int kOddRow = RH | 1;
+    __syncwarp();
+#pragma unroll 4
+    for (int k = 0; k < 2 * RH; ++k) {
+      int v = -16384 - go;  // padding rows below the query never score
+      if ((uint32_t)k < L) v = (int)matT[(int)query[k] * 32 + lane] - go;
+      prof[(k < RH ? k : k - RH + kOddRow) * 32 + lane] = (uint16_t)v;
+    }
+    __syncwarp();
+    const uint16_t *myprof = prof + odd * (kOddRow * 32);
+
+    uint32_t best = go_pk;           // running max of H+open over this lane's rows, per half
+    uint32_t enda = 0, endb = 0;     // column of the last maximum (aligner.cpp:650-653)
+    uint32_t hgo[RH], e[RH];
+#pragma unroll
+    for (int k = 0; k < RH; ++k) { hgo[k] = go_pk; e[k] = 0u; }          // aligner.cpp:587-590
+    uint32_t top_prev = go_pk;       // H+open of the row above this lane's rows, previous column
+    uint32_t send_top = go_pk, send_f = gef_pk;
+    // the odd lane is one column behind: at step t it works on column t - 1 (nothing at t = 0)
+    uint32_t ca = (!odd && wa > 0) ? pa[0] : (uint32_t)kSeqEnd, cb = (!odd && wb > 0) ? pb[0] : (uint32_t)kSeqEnd;
+
+    for (uint32_t t = 0; t <= wmax; ++t) {
+      const uint32_t j = t - odd;                       // this lane's column (wraps for the odd lane at t = 0)
+      const uint32_t jn = j + 1;                        // next column; columns beyond a window read as SEQUENCE_END
+      const uint32_t na = (jn < wa) ? pa[jn] : (uint32_t)kSeqEnd;
+      const uint32_t nb = (jn < wb) ? pb[jn] : (uint32_t)kSeqEnd;
+      // what left the even lane's last row at this column, one step ago
+      const uint32_t recv_top = __shfl_up_sync(kFull, send_top, 1);
+      const uint32_t recv_f = __shfl_up_sync(kFull, send_f, 1);
+      const uint32_t top = odd ? recv_top : go_pk;
+      uint32_t f = odd ? recv_f : gef_pk;
+      uint32_t cmax = 0x80008000u;
+      const uint16_t *ta = myprof + ca, *tb = myprof + cb;
+      e[0] = __viaddmax_s16x2(e[0], ge_pk, hgo[0]);                      // aligner.cpp:623-627
+      uint32_t m = __viaddmax_s16x2_relu(                                 // :617-620,:629-631
+          top_prev, (uint32_t)tb[0] * 65536u + (uint32_t)ta[0], e[0]);
+#pragma unroll
+      for (int k = 0; k < RH; ++k) {
+        uint32_t m_next = 0;
+        if (k + 1 < RH) {
+          const uint32_t s = (uint32_t)tb[(k + 1) * 32] * 65536u + (uint32_t)ta[(k + 1) * 32];
+          e[k + 1] = __viaddmax_s16x2(e[k + 1], ge_pk, hgo[k + 1]);
+          m_next = __viaddmax_s16x2_relu(hgo[k], s, e[k + 1]);
+        }
+        const uint32_t mgo = __vadd2(m, go_pk);
+        hgo[k] = __viaddmax_s16x2(f, go_pk, mgo);                        // H = max(m, F)  :641-643
+        f = __viaddmax_s16x2(f, gef_pk, mgo);                            // :634-639
+        cmax = __vmaxs2(cmax, hgo[k]);
+        m = m_next;
+      }
+      const bool xa = ca == kSeqEnd, xb = cb == kSeqEnd;
+      if (__any_sync(kFull, xa | xb)) {                                  // aligner.cpp:664-669
+        const uint32_t keep = (xa ? 0u : 0x0000FFFFu) | (xb ? 0u : 0xFFFF0000u);
+        const uint32_t rst = go_pk & ~keep;
+#pragma unroll
+        for (int k = 0; k < RH; ++k) {
+          hgo[k] = (hgo[k] & keep) | rst;
+          e[k] &= keep;
+        }
+        cmax = (cmax & keep) | (0x80008000u & ~keep);
+      }
+      top_prev = top;
+      send_top = hgo[RH - 1];
+      send_f = f;
+      bool ph, pl;
+      best = __vibmax_s16x2(cmax, best, &ph, &pl);                      // ">=": last maximum wins
+      if (pl) enda = j;
+      if (ph) endb = j;
+      ca = na;
+      cb = nb;
+    }
+    // the candidate's result: the larger of the two lanes' maxima, on a tie the later column
+    {
+      const uint32_t obest = __shfl_xor_sync(kFull, best, 1);
+      const uint32_t oenda = __shfl_xor_sync(kFull, enda, 1), oendb = __shfl_xor_sync(kFull, endb, 1);
+      const int ma = (int)(int16_t)(best & 0xFFFFu), oa = (int)(int16_t)(obest & 0xFFFFu);
+      const int mb = (int)(int16_t)(best >> 16), ob = (int)(int16_t)(obest >> 16);
+      const int ra = ma > oa ? ma : oa, rb = mb > ob ? mb : ob;
+      const uint32_t fa = ma > oa ? enda : (oa > ma ? oenda : max(enda, oenda));
+      const uint32_t fb = mb > ob ? endb : (ob > mb ? oendb : max(endb, oendb));
+      if (!odd) {
+        if (ia < cnt) {
+          p.cand_score[off + ia] = (uint32_t)(ra - go);
+          p.cand_end[off + ia] = offa + fa;
+        }
+        if (ib < cnt) {
+          p.cand_score[off + ib] = (uint32_t)(rb - go);
+          p.cand_end[off + ib] = offb + fb;
+        }
+      }
+    }
+    const unsigned long long cells =
+        (unsigned long long)__reduce_add_sync(kFull, odd ? 0u : wa + wb) * (unsigned long long)L;
+    if (lane == 0) atomicAdd(p.cells, cells);
+  }
+}
+
 // One thread per candidate, 32-bit scores, DP columns in local memory: the direct form of the
 // reference loop.  Used when the packed s16 kernel's score range check fails (exotic matrices).
 __global__ void __launch_bounds__(128) sw_extend_s32_kernel(const SwParams p) {
@@ -230,18 +391,58 @@ cudaError_t launch_dpx(const SwParams &p, int sm_count, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+template <int RH>
+cudaError_t launch_pair(const SwParams &p, int sm_count, cudaStream_t stream) {
+  const size_t smem = 2048 + (size_t)kSwWarps * (2 * RH + 1) * 32 * sizeof(uint16_t);
+  cudaError_t err = allow_max_dynamic_smem(sw_extend_pair_kernel<RH>);
+  if (err != cudaSuccess) return err;
+  sw_extend_pair_kernel<RH><<<sm_count * 2, kSwThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace
+
+// Rows per lane of the pair kernel (two lanes per candidate pair, 32 candidates per warp task) for a
+// query length, or 0 when the strip kernel is to be used.
+int sw_pair_rows(uint32_t query_len) {
+  static const int on = [] { const char *e = getenv("GM_SW_PAIR"); return e ? atoi(e) : 1; }();
+  if (!on || query_len <= 40 || query_len > 80) return 0;
+  static const int kHalf[] = {24, 28, 32, 36, 38, 40};
+  for (int r : kHalf)
+    if ((uint32_t)(2 * r) >= query_len) return r;
+  return 0;
+}
+
+cudaError_t sw_extend_pair_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream) {
+  switch (rows) {
+    case 24: return launch_pair<24>(p, sm_count, stream);
+    case 28: return launch_pair<28>(p, sm_count, stream);
+    case 32: return launch_pair<32>(p, sm_count, stream);
+    case 36: return launch_pair<36>(p, sm_count, stream);
+    case 38: return launch_pair<38>(p, sm_count, stream);
+    case 40: return launch_pair<40>(p, sm_count, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
 
 // rows per strip for a query length: the smallest instantiated R that covers L in
 // ceil(L / kSwMaxRows) strips.
 int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips) {
-  static const int kRows[] = {16, 32, 40, 48, 64, 75, 80};
+  static const int kRows[] = {16, 25, 32, 38, 40, 48, 64, 75, 80};
   if (const char *env = getenv("GM_SW_ROWS")) {  // tuning experiments: force rows per strip
     const int r = atoi(env);
     for (int k : kRows)
       if (k == r) { *n_strips = (query_len + r - 1) / r; return r; }
   }
   const uint32_t strips = (query_len + kSwMaxRows - 1) / kSwMaxRows;
+  if (strips == 1 && query_len > 64) {
+    // two half-height strips at 128 registers (4 warps per scheduler instead of 2) beat one full-height
+    // strip when they fit the query almost exactly: L = 75 runs 2 x 38 rows at 4.58 instead of 4.47 TCUPS
+    // in spite of the boundary row going through the L2 scratch
+    const uint32_t half = (query_len + 1) / 2;
+    for (int r : kRows)
+      if ((uint32_t)r >= half && r <= 40 && 2u * r * 100u <= query_len * 102u) { *n_strips = 2; return r; }
+  }
   const uint32_t need = (query_len + strips - 1) / strips;
   for (int r : kRows)
     if ((uint32_t)r >= need) { *n_strips = (query_len + r - 1) / r; return r; }
@@ -252,7 +453,9 @@ int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips) {
 cudaError_t sw_extend_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream) {
   switch (rows) {
     case 16: return launch_dpx<16>(p, sm_count, stream);
+    case 25: return launch_dpx<25>(p, sm_count, stream);
     case 32: return launch_dpx<32>(p, sm_count, stream);
+    case 38: return launch_dpx<38>(p, sm_count, stream);
     case 40: return launch_dpx<40>(p, sm_count, stream);
     case 48: return launch_dpx<48>(p, sm_count, stream);
     case 64: return launch_dpx<64>(p, sm_count, stream);
