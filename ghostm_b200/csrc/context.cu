@@ -14,7 +14,7 @@ namespace gm {
 
 // ---- kernels defined in the other translation units -----------------------------------
 int sw_rows_per_strip(uint32_t query_len, uint32_t *n_strips);
-int sw_pair_rows(uint32_t query_len);
+int sw_pair_rows(uint32_t query_len, uint32_t *n_strips);
 cudaError_t sw_extend_pair_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream);
 cudaError_t sw_extend_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream);
 cudaError_t sw_extend_s32_launch(const SwParams &p, int sm_count, cudaStream_t stream);
@@ -992,8 +992,10 @@ int score_impl(gm_context *c, uint32_t first, uint32_t end, uint32_t *scores, ui
   DbChunk &ch = c->chunks[c->cur_chunk];
   GM_CUDA(c->cand_score.ensure(c->cand_capacity));
   GM_CUDA(c->cand_end.ensure(c->cand_capacity));
-  uint32_t n_strips = 1;
+  uint32_t n_strips = 1, pair_strips = 1;
   const int rows = sw_rows_per_strip(c->query_len, &n_strips);
+  const int pair_rows = c->use_s32 ? 0 : sw_pair_rows(c->query_len, &pair_strips);
+  if (pair_rows) n_strips = pair_strips;
   SwParams p = {};
   p.db = ch.seq.p;
   p.db_len = ch.seq_len;
@@ -1025,7 +1027,7 @@ int score_impl(gm_context *c, uint32_t first, uint32_t end, uint32_t *scores, ui
       GM_CUDA(c->strip_scratch.ensure(need));
     }
     p.strip_scratch = c->strip_scratch.p;
-    if (const int pair_rows = sw_pair_rows(c->query_len)) {   // two lanes per candidate pair, 32 candidates per task
+    if (pair_rows) {   // two lanes per candidate pair, 32 candidates per task
       if (int r = scan_counts(c, first, end, 2, nullptr)) return r;
       GM_CUDA(sw_extend_pair_launch(p, pair_rows, c->sm_count, c->stream));
     } else {

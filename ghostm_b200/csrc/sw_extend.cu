@@ -179,7 +179,18 @@ __global__ void __launch_bounds__(kSwThreads, (R <= 40 ? 2 : 1)) sw_extend_dpx_k
   }
 }
 
-// Pair variant for queries of 41..80 residues: TWO adjacent lanes share a pair of candidates, the even
+// (max, last column) of two disjoint sets of DP cells, per packed half: the larger maximum, on a tie
+// the later column (aligner.cpp:650-653 keeps the LAST column that attains the maximum).
+__device__ __forceinline__ void merge_max(uint32_t &best, uint32_t &enda, uint32_t &endb, uint32_t obest,
+                                          uint32_t oenda, uint32_t oendb) {
+  const int ma = (int)(int16_t)(best & 0xFFFFu), oa = (int)(int16_t)(obest & 0xFFFFu);
+  const int mb = (int)(int16_t)(best >> 16), ob = (int)(int16_t)(obest >> 16);
+  enda = ma > oa ? enda : (oa > ma ? oenda : max(enda, oenda));
+  endb = mb > ob ? endb : (ob > mb ? oendb : max(endb, oendb));
+  best = ((uint32_t)(mb > ob ? mb : ob) << 16) | ((uint32_t)(ma > oa ? ma : oa) & 0xFFFFu);
+}
+
+// Pair variant for queries of 41 residues and more: TWO adjacent lanes share a pair of candidates, the even
 // lane holds rows [0, RH) and the odd lane rows [RH, 2 RH) of the same DP, one column behind (a
 // two-stage systolic array): what leaves the even lane's last row at column j - H+open and the
 // vertical F - reaches the odd lane by one shuffle each and is consumed at its column j one step
@@ -240,97 +251,115 @@ __global__ void __launch_bounds__(kSwThreads, 2) sw_extend_pair_kernel(const SwP
     const uint8_t *pa = p.db + offa, *pb = p.db + offb;
     const uint32_t wmax = __reduce_max_sync(kFull, wa > wb ? wa : wb);
 
-    // per-warp query profile T[k][c] = matrix[c][query[k]] - open for the 2 RH rows.  A table row is
-    // 64 bytes = 16 banks; the odd lanes' half starts at an ODD table row, so that in every load the
-    // even lanes (row k) and the odd lanes (row k + RH) hit different halves of the 32 banks
-    constexpr int kOddRow = RH | 1;
-    __syncwarp();
-#pragma unroll 4
-    for (int k = 0; k < 2 * RH; ++k) {
-      int v = -16384 - go;  // padding rows below the query never score
-      if ((uint32_t)k < L) v = (int)matT[(int)query[k] * 32 + lane] - go;
-      prof[(k < RH ? k : k - RH + kOddRow) * 32 + lane] = (uint16_t)v;
-    }
-    __syncwarp();
-    const uint16_t *myprof = prof + odd * (kOddRow * 32);
-
-    uint32_t best = go_pk;           // running max of H+open over this lane's rows, per half
+    uint32_t best = go_pk;           // running max of H+open over this lane's rows (all strips), per half
     uint32_t enda = 0, endb = 0;     // column of the last maximum (aligner.cpp:650-653)
-    uint32_t hgo[RH], e[RH];
-#pragma unroll
-    for (int k = 0; k < RH; ++k) { hgo[k] = go_pk; e[k] = 0u; }          // aligner.cpp:587-590
-    uint32_t top_prev = go_pk;       // H+open of the row above this lane's rows, previous column
-    uint32_t send_top = go_pk, send_f = gef_pk;
-    // the odd lane is one column behind: at step t it works on column t - 1 (nothing at t = 0)
-    uint32_t ca = (!odd && wa > 0) ? pa[0] : (uint32_t)kSeqEnd, cb = (!odd && wb > 0) ? pb[0] : (uint32_t)kSeqEnd;
+    // the boundary row between two strips of 2 RH rows: (H+open, F) per column and lane pair, L2 resident
+    uint32_t *scr = p.strip_scratch + (size_t)(blockIdx.x * kSwWarps + warp) * p.base_len * 32 + (lane >> 1);
+    constexpr int kOddRow = RH | 1;
 
-    for (uint32_t t = 0; t <= wmax; ++t) {
-      const uint32_t j = t - odd;                       // this lane's column (wraps for the odd lane at t = 0)
-      const uint32_t jn = j + 1;                        // next column; columns beyond a window read as SEQUENCE_END
-      const uint32_t na = (jn < wa) ? pa[jn] : (uint32_t)kSeqEnd;
-      const uint32_t nb = (jn < wb) ? pb[jn] : (uint32_t)kSeqEnd;
-      // what left the even lane's last row at this column, one step ago
-      const uint32_t recv_top = __shfl_up_sync(kFull, send_top, 1);
-      const uint32_t recv_f = __shfl_up_sync(kFull, send_f, 1);
-      const uint32_t top = odd ? recv_top : go_pk;
-      uint32_t f = odd ? recv_f : gef_pk;
-      uint32_t cmax = 0x80008000u;
-      const uint16_t *ta = myprof + ca, *tb = myprof + cb;
-      e[0] = __viaddmax_s16x2(e[0], ge_pk, hgo[0]);                      // aligner.cpp:623-627
-      uint32_t m = __viaddmax_s16x2_relu(                                 // :617-620,:629-631
-          top_prev, (uint32_t)tb[0] * 65536u + (uint32_t)ta[0], e[0]);
-#pragma unroll
-      for (int k = 0; k < RH; ++k) {
-        uint32_t m_next = 0;
-        if (k + 1 < RH) {
-          const uint32_t s = (uint32_t)tb[(k + 1) * 32] * 65536u + (uint32_t)ta[(k + 1) * 32];
-          e[k + 1] = __viaddmax_s16x2(e[k + 1], ge_pk, hgo[k + 1]);
-          m_next = __viaddmax_s16x2_relu(hgo[k], s, e[k + 1]);
-        }
-        const uint32_t mgo = __vadd2(m, go_pk);
-        hgo[k] = __viaddmax_s16x2(f, go_pk, mgo);                        // H = max(m, F)  :641-643
-        f = __viaddmax_s16x2(f, gef_pk, mgo);                            // :634-639
-        cmax = __vmaxs2(cmax, hgo[k]);
-        m = m_next;
+    for (uint32_t strip = 0; strip < p.n_strips; ++strip) {
+      // per-warp query profile T[k][c] = matrix[c][query[row]] - open for the 2 RH rows of the strip.
+      // A table row is 64 bytes = 16 banks; the odd lanes' half starts at an ODD table row, so that in
+      // every load the even lanes (row k) and the odd lanes (row k + RH) hit different halves of the
+      // 32 banks
+      __syncwarp();
+#pragma unroll 4
+      for (int k = 0; k < 2 * RH; ++k) {
+        const uint32_t row = strip * (2 * RH) + k;
+        int v = -16384 - go;  // padding rows below the query never score
+        if (row < L) v = (int)matT[(int)query[row] * 32 + lane] - go;
+        prof[(k < RH ? k : k - RH + kOddRow) * 32 + lane] = (uint16_t)v;
       }
-      const bool xa = ca == kSeqEnd, xb = cb == kSeqEnd;
-      if (__any_sync(kFull, xa | xb)) {                                  // aligner.cpp:664-669
-        const uint32_t keep = (xa ? 0u : 0x0000FFFFu) | (xb ? 0u : 0xFFFF0000u);
-        const uint32_t rst = go_pk & ~keep;
+      __syncwarp();
+      const uint16_t *myprof = prof + odd * (kOddRow * 32);
+      const bool first_strip = strip == 0, last_strip = strip + 1 == p.n_strips;
+
+      uint32_t hgo[RH], e[RH];
+#pragma unroll
+      for (int k = 0; k < RH; ++k) { hgo[k] = go_pk; e[k] = 0u; }        // aligner.cpp:587-590
+      uint32_t top_prev = go_pk;       // H+open of the row above this lane's rows, previous column
+      uint32_t send_top = go_pk, send_f = gef_pk;
+      // maximum of THIS strip's rows and its last column (">=" in column order); merged below, because
+      // a later strip may reach the same maximum in an earlier column
+      uint32_t sbest = go_pk, sea = 0, seb = 0;
+      // the odd lane is one column behind: at step t it works on column t - 1 (nothing at t = 0)
+      uint32_t ca = (!odd && wa > 0) ? pa[0] : (uint32_t)kSeqEnd, cb = (!odd && wb > 0) ? pb[0] : (uint32_t)kSeqEnd;
+
+      for (uint32_t t = 0; t <= wmax; ++t) {
+        const uint32_t j = t - odd;                     // this lane's column (wraps for the odd lane at t = 0)
+        const uint32_t jn = j + 1;                      // next column; columns beyond a window read as SEQUENCE_END
+        const uint32_t na = (jn < wa) ? pa[jn] : (uint32_t)kSeqEnd;
+        const uint32_t nb = (jn < wb) ? pb[jn] : (uint32_t)kSeqEnd;
+        // what left the even lane's last row at this column, one step ago
+        const uint32_t recv_top = __shfl_up_sync(kFull, send_top, 1);
+        const uint32_t recv_f = __shfl_up_sync(kFull, send_f, 1);
+        uint32_t top = go_pk, f = gef_pk;
+        if (odd) {
+          top = recv_top;
+          f = recv_f;
+        } else if (!first_strip && j < wmax) {          // the strip above, same column
+          top = scr[(j * 2 + 0) * 16];
+          f = scr[(j * 2 + 1) * 16];
+        }
+        uint32_t cmax = 0x80008000u;
+        const uint16_t *ta = myprof + ca, *tb = myprof + cb;
+        e[0] = __viaddmax_s16x2(e[0], ge_pk, hgo[0]);                    // aligner.cpp:623-627
+        uint32_t m = __viaddmax_s16x2_relu(                               // :617-620,:629-631
+            top_prev, (uint32_t)tb[0] * 65536u + (uint32_t)ta[0], e[0]);
 #pragma unroll
         for (int k = 0; k < RH; ++k) {
-          hgo[k] = (hgo[k] & keep) | rst;
-          e[k] &= keep;
+          uint32_t m_next = 0;
+          if (k + 1 < RH) {
+            const uint32_t s = (uint32_t)tb[(k + 1) * 32] * 65536u + (uint32_t)ta[(k + 1) * 32];
+            e[k + 1] = __viaddmax_s16x2(e[k + 1], ge_pk, hgo[k + 1]);
+            m_next = __viaddmax_s16x2_relu(hgo[k], s, e[k + 1]);
+          }
+          const uint32_t mgo = __vadd2(m, go_pk);
+          hgo[k] = __viaddmax_s16x2(f, go_pk, mgo);                      // H = max(m, F)  :641-643
+          f = __viaddmax_s16x2(f, gef_pk, mgo);                          // :634-639
+          cmax = __vmaxs2(cmax, hgo[k]);
+          m = m_next;
         }
-        cmax = (cmax & keep) | (0x80008000u & ~keep);
+        const bool xa = ca == kSeqEnd, xb = cb == kSeqEnd;
+        if (__any_sync(kFull, xa | xb)) {                                // aligner.cpp:664-669
+          const uint32_t keep = (xa ? 0u : 0x0000FFFFu) | (xb ? 0u : 0xFFFF0000u);
+          const uint32_t rst = go_pk & ~keep;
+#pragma unroll
+          for (int k = 0; k < RH; ++k) {
+            hgo[k] = (hgo[k] & keep) | rst;
+            e[k] &= keep;
+          }
+          cmax = (cmax & keep) | (0x80008000u & ~keep);
+        }
+        top_prev = top;
+        send_top = hgo[RH - 1];
+        send_f = f;
+        if (odd && !last_strip && j < wmax) {           // bottom row of the strip for the strip below
+          scr[(j * 2 + 0) * 16] = hgo[RH - 1];
+          scr[(j * 2 + 1) * 16] = f;
+        }
+        bool ph, pl;
+        sbest = __vibmax_s16x2(cmax, sbest, &ph, &pl);                  // ">=": last maximum wins
+        if (pl) sea = j;
+        if (ph) seb = j;
+        ca = na;
+        cb = nb;
       }
-      top_prev = top;
-      send_top = hgo[RH - 1];
-      send_f = f;
-      bool ph, pl;
-      best = __vibmax_s16x2(cmax, best, &ph, &pl);                      // ">=": last maximum wins
-      if (pl) enda = j;
-      if (ph) endb = j;
-      ca = na;
-      cb = nb;
+      merge_max(best, enda, endb, sbest, sea, seb);
     }
     // the candidate's result: the larger of the two lanes' maxima, on a tie the later column
     {
       const uint32_t obest = __shfl_xor_sync(kFull, best, 1);
       const uint32_t oenda = __shfl_xor_sync(kFull, enda, 1), oendb = __shfl_xor_sync(kFull, endb, 1);
-      const int ma = (int)(int16_t)(best & 0xFFFFu), oa = (int)(int16_t)(obest & 0xFFFFu);
-      const int mb = (int)(int16_t)(best >> 16), ob = (int)(int16_t)(obest >> 16);
-      const int ra = ma > oa ? ma : oa, rb = mb > ob ? mb : ob;
-      const uint32_t fa = ma > oa ? enda : (oa > ma ? oenda : max(enda, oenda));
-      const uint32_t fb = mb > ob ? endb : (ob > mb ? oendb : max(endb, oendb));
+      merge_max(best, enda, endb, obest, oenda, oendb);
       if (!odd) {
         if (ia < cnt) {
-          p.cand_score[off + ia] = (uint32_t)(ra - go);
-          p.cand_end[off + ia] = offa + fa;
+          p.cand_score[off + ia] = (uint32_t)((int)(int16_t)(best & 0xFFFFu) - go);
+          p.cand_end[off + ia] = offa + enda;
         }
         if (ib < cnt) {
-          p.cand_score[off + ib] = (uint32_t)(rb - go);
-          p.cand_end[off + ib] = offb + fb;
+          p.cand_score[off + ib] = (uint32_t)((int)(int16_t)(best >> 16) - go);
+          p.cand_end[off + ib] = offb + endb;
         }
       }
     }
@@ -402,15 +431,25 @@ cudaError_t launch_pair(const SwParams &p, int sm_count, cudaStream_t stream) {
 
 }  // namespace
 
-// Rows per lane of the pair kernel (two lanes per candidate pair, 32 candidates per warp task) for a
-// query length, or 0 when the strip kernel is to be used.
-int sw_pair_rows(uint32_t query_len) {
+// Rows per lane of the pair kernel (two lanes per candidate pair, 32 candidates per warp task) and the
+// number of strips of 2 x rows for a query length; 0 when the single-lane kernel is to be used
+// (queries of up to 40 residues already run at 128 registers there).
+int sw_pair_rows(uint32_t query_len, uint32_t *n_strips) {
   static const int on = [] { const char *e = getenv("GM_SW_PAIR"); return e ? atoi(e) : 1; }();
-  if (!on || query_len <= 40 || query_len > 80) return 0;
+  if (!on || query_len <= 40) return 0;
   static const int kHalf[] = {24, 28, 32, 36, 38, 40};
-  for (int r : kHalf)
-    if ((uint32_t)(2 * r) >= query_len) return r;
-  return 0;
+  int best = 0;
+  uint32_t best_rows = 0, best_strips = 0;
+  for (int r : kHalf) {      // fewest padded rows; among equals the taller strip (fewer boundary rows)
+    const uint32_t strips = (query_len + 2 * r - 1) / (2 * r), rows = strips * 2 * r;
+    if (best == 0 || rows < best_rows || (rows == best_rows && strips <= best_strips)) {
+      best = r;
+      best_rows = rows;
+      best_strips = strips;
+    }
+  }
+  *n_strips = best_strips;
+  return best;
 }
 
 cudaError_t sw_extend_pair_launch(const SwParams &p, int rows, int sm_count, cudaStream_t stream) {
