@@ -199,7 +199,7 @@ __device__ __forceinline__ void merge_max(uint32_t &best, uint32_t &enda, uint32
 // sends it through an L2 scratch and walks the window twice), and each lane keeps its own running
 // maximum: (max, last column) of the candidate is the larger of the two, on a tie the later column.
 // One warp task = 32 candidates of one query.
-template <int RH>
+template <int RH, bool ONE_STRIP>
 __global__ void __launch_bounds__(kSwThreads, 2) sw_extend_pair_kernel(const SwParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int16_t *matT = reinterpret_cast<int16_t *>(smem_raw);                 // [query residue][db residue]
@@ -254,10 +254,12 @@ __global__ void __launch_bounds__(kSwThreads, 2) sw_extend_pair_kernel(const SwP
     uint32_t best = go_pk;           // running max of H+open over this lane's rows (all strips), per half
     uint32_t enda = 0, endb = 0;     // column of the last maximum (aligner.cpp:650-653)
     // the boundary row between two strips of 2 RH rows: (H+open, F) per column and lane pair, L2 resident
-    uint32_t *scr = p.strip_scratch + (size_t)(blockIdx.x * kSwWarps + warp) * p.base_len * 32 + (lane >> 1);
+    uint32_t *scr = ONE_STRIP ? nullptr
+                              : p.strip_scratch + (size_t)(blockIdx.x * kSwWarps + warp) * p.base_len * 32 + (lane >> 1);
     constexpr int kOddRow = RH | 1;
 
-    for (uint32_t strip = 0; strip < p.n_strips; ++strip) {
+    const uint32_t n_strips = ONE_STRIP ? 1u : p.n_strips;
+    for (uint32_t strip = 0; strip < n_strips; ++strip) {
       // per-warp query profile T[k][c] = matrix[c][query[row]] - open for the 2 RH rows of the strip.
       // A table row is 64 bytes = 16 banks; the odd lanes' half starts at an ODD table row, so that in
       // every load the even lanes (row k) and the odd lanes (row k + RH) hit different halves of the
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kSwThreads, 2) sw_extend_pair_kernel(const SwP
       }
       __syncwarp();
       const uint16_t *myprof = prof + odd * (kOddRow * 32);
-      const bool first_strip = strip == 0, last_strip = strip + 1 == p.n_strips;
+      const bool first_strip = ONE_STRIP || strip == 0, last_strip = ONE_STRIP || strip + 1 == n_strips;
 
       uint32_t hgo[RH], e[RH];
 #pragma unroll
@@ -423,9 +425,14 @@ cudaError_t launch_dpx(const SwParams &p, int sm_count, cudaStream_t stream) {
 template <int RH>
 cudaError_t launch_pair(const SwParams &p, int sm_count, cudaStream_t stream) {
   const size_t smem = 2048 + (size_t)kSwWarps * (2 * RH + 1) * 32 * sizeof(uint16_t);
-  cudaError_t err = allow_max_dynamic_smem(sw_extend_pair_kernel<RH>);
-  if (err != cudaSuccess) return err;
-  sw_extend_pair_kernel<RH><<<sm_count * 2, kSwThreads, smem, stream>>>(p);
+  cudaError_t err;
+  if (p.n_strips == 1) {
+    if ((err = allow_max_dynamic_smem(sw_extend_pair_kernel<RH, true>)) != cudaSuccess) return err;
+    sw_extend_pair_kernel<RH, true><<<sm_count * 2, kSwThreads, smem, stream>>>(p);
+  } else {
+    if ((err = allow_max_dynamic_smem(sw_extend_pair_kernel<RH, false>)) != cudaSuccess) return err;
+    sw_extend_pair_kernel<RH, false><<<sm_count * 2, kSwThreads, smem, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 
