@@ -342,7 +342,7 @@ def rooflines(spec, st, n_launch_front, dpx_rate):
     traffic = _measured_traffic()
     sw_t, se_t = traffic.get(spec.name + ":sw_extend"), traffic.get(spec.name + ":seed_search")
     window = spec.length + 2 * 2 + 2 * 16
-    return ({"bound": "int_dpx", "kernel": "sw_extend_dpx_kernel", "achieved": achieved, "peak": peak,
+    return ({"bound": "int_dpx", "kernel": "sw_extend_pair_kernel (41 <= L), sw_extend_dpx_kernel (L <= 40)", "achieved": achieved, "peak": peak,
              "unit": "Tint-op/s", "frac": achieved / peak if peak else None,
              "traffic": sw_t["dram_bytes_per_candidate"] * cand_per_launch if sw_t else None,
              "traffic_source": sw_t["source"] if sw_t else None,
