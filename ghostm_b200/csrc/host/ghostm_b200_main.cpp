@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <condition_variable>
+#include <functional>
 #include <fstream>
 #include <iostream>
 #include <mutex>
@@ -527,42 +528,97 @@ int run_aln(int argc, char **argv) {
                                   name_break.data() + base), "gm_query_upload");
           }
         });
-        for (uint32_t round0 = 0; round0 < n_chunks; round0 += (uint32_t)n_dev) {
-          on_every_device(shards, [&](size_t d) {          // front: the owned chunk of this round
-            const uint32_t c = round0 + (uint32_t)d;
-            shards[d].segs.clear();
-            memset(&shards[d].stats, 0, sizeof(gm_stats));
-            const clock_t t0 = clock();
-            if (c < n_chunks)
-              shards[d].segs = front_chunk(shards[d].front, c, q.n, o.max_list_length, &shards[d].capacity,
-                                           &shards[d].stats);
-            (void)t0;
+        // Pipeline over the rounds of n_dev chunks: per device a FRONT thread (seed search + SW of the
+        // owned chunk) and a BACK thread (candidate transfer + Merge calls of the device's query slice).
+        // The front of round k+1 starts as soon as every back has FETCHED round k's candidates from
+        // this front (gm_candidates_transfer reads the front context's buffers); the Merge calls of
+        // round k run under it.  A front context is never used by two threads at once: transfers of a
+        // round start after its front has finished and the next front waits for them.
+        const uint32_t n_rounds = (n_chunks + (uint32_t)n_dev - 1) / (uint32_t)n_dev;
+        std::vector<std::vector<std::vector<Segment>>> segs(n_dev, std::vector<std::vector<Segment>>(n_rounds));
+        std::vector<std::vector<gm_stats>> round_stats(n_dev, std::vector<gm_stats>(n_rounds));
+        std::vector<uint32_t> front_done(n_dev, 0);        // rounds whose front stage is finished, per device
+        std::vector<uint32_t> fetched(n_dev, 0);           // transfers taken from this front, all rounds so far
+        uint32_t n_backs = 0;
+        for (size_t r = 0; r < n_dev; ++r) n_backs += bounds[r + 1] > bounds[r];
+        std::mutex mu;
+        std::condition_variable cv;
+        bool failed = false;
+        std::vector<std::thread> workers;
+        auto guarded = [&](size_t d, const std::function<void()> &body) {
+          try {
+            body();
+          } catch (std::exception &e) {
+            std::lock_guard<std::mutex> lock(mu);
+            if (shards[d].error.empty()) shards[d].error = e.what();
+            failed = true;
+            cv.notify_all();
+          }
+        };
+        for (size_t d = 0; d < n_dev; ++d) {
+          workers.emplace_back([&, d] {                    // front thread of device d
+            guarded(d, [&] {
+              for (uint32_t k = 0; k < n_rounds; ++k) {
+                {
+                  std::unique_lock<std::mutex> lock(mu);   // every back has taken round k-1 from this front
+                  cv.wait(lock, [&] { return failed || fetched[d] >= k * n_backs; });
+                  if (failed) return;
+                }
+                const uint32_t c = k * (uint32_t)n_dev + (uint32_t)d;
+                memset(&round_stats[d][k], 0, sizeof(gm_stats));
+                if (c < n_chunks)
+                  segs[d][k] = front_chunk(shards[d].front, c, q.n, o.max_list_length, &shards[d].capacity,
+                                           &round_stats[d][k]);
+                std::lock_guard<std::mutex> lock(mu);
+                front_done[d] = k + 1;
+                cv.notify_all();
+              }
+            });
           });
-          if (o.verbose)
-            for (size_t d = 0; d < n_dev; ++d)
-              if (round0 + d < n_chunks) report(round0 + (uint32_t)d, shards[d].stats, 0.0);
-          on_every_device(shards, [&](size_t r) {          // back: the round's chunks, ascending
+          workers.emplace_back([&, d] {                    // back thread of device d: its slice, chunks ascending
+            const size_t r = d;
             const uint32_t base = bounds[r], stop = bounds[r + 1];
             if (stop == base) return;
-            for (size_t s = 0; s < n_dev; ++s) {
-              const uint32_t c = round0 + (uint32_t)s;
-              if (c >= n_chunks) break;
-              if (shards[s].segs.empty()) continue;        // empty list: no Merge call (aligner.cpp:136)
-              {
-                std::lock_guard<std::mutex> lock(shards[s].front_mu);
-                uint64_t back_cap = std::max(shards[r].capacity, shards[s].capacity);
-                check(gm_set_candidate_capacity(shards[r].back, back_cap), "gm_set_candidate_capacity");
-                check(gm_candidates_transfer(shards[s].front, shards[r].back, c, base, stop),
-                      "gm_candidates_transfer");
+            guarded(r, [&] {
+              for (uint32_t k = 0; k < n_rounds; ++k) {
+                for (size_t s = 0; s < n_dev; ++s) {
+                  const uint32_t c = k * (uint32_t)n_dev + (uint32_t)s;
+                  {
+                    std::unique_lock<std::mutex> lock(mu);
+                    cv.wait(lock, [&] { return failed || front_done[s] > k; });
+                    if (failed) return;
+                  }
+                  const bool work = c < n_chunks && !segs[s][k].empty();   // empty list: no Merge call (aligner.cpp:136)
+                  if (work) {
+                    std::lock_guard<std::mutex> lock(shards[s].front_mu);
+                    const uint64_t back_cap = std::max(shards[r].capacity, shards[s].capacity);
+                    check(gm_set_candidate_capacity(shards[r].back, back_cap), "gm_set_candidate_capacity");
+                    check(gm_candidates_transfer(shards[s].front, shards[r].back, c, base, stop),
+                          "gm_candidates_transfer");
+                  }
+                  {
+                    std::lock_guard<std::mutex> lock(mu);
+                    ++fetched[s];
+                    cv.notify_all();
+                  }
+                  if (!work) continue;
+                  for (const Segment &g : segs[s][k]) {      // one Merge call per candidate chunk
+                    uint32_t f = std::min(std::max(g.first, base), stop), e = std::max(std::min(g.end, stop), base);
+                    if (f >= e) f = e = base;                // carried lists only (aligner.cpp:702)
+                    check(gm_merge(shards[r].back, f - base, e - base, nullptr), "gm_merge");
+                  }
+                }
               }
-              for (const Segment &g : shards[s].segs) {    // one Merge call per candidate chunk
-                uint32_t f = std::min(std::max(g.first, base), stop), e = std::max(std::min(g.end, stop), base);
-                if (f >= e) f = e = base;                  // carried lists only (aligner.cpp:702)
-                check(gm_merge(shards[r].back, f - base, e - base, nullptr), "gm_merge");
-              }
-            }
+            });
           });
         }
+        for (auto &w : workers) w.join();
+        for (auto &sh : shards)
+          if (!sh.error.empty()) throw DeviceError(sh.error);
+        if (o.verbose)
+          for (uint32_t k = 0; k < n_rounds; ++k)
+            for (size_t d = 0; d < n_dev; ++d)
+              if (k * n_dev + d < n_chunks) report(k * (uint32_t)n_dev + (uint32_t)d, round_stats[d][k], 0.0);
         on_every_device(shards, [&](size_t r) {            // TraceBack of the survivors, lists home
           const uint32_t base = bounds[r], stop = bounds[r + 1];
           if (stop == base) return;
