@@ -1452,7 +1452,8 @@ extern "C" int gm_wait(gm_context *c, gm_stats *stats) {
 // runs the deferred TraceBack of the survivors.
 extern "C" int gm_query_upload_async(gm_context *c, const uint8_t *seqs, uint32_t n, uint32_t L,
                                      const uint8_t *name_break) {
-  if (c && c->async_open)
+  if (int r = check_ctx(c)) return r;
+  if (c->async_open)
     if (int r = gm_wait(c, nullptr)) return r;   // a new batch replaces the lists the old one still merges into
   c->no_sync_upload = true;
   const int r = gm_query_upload(c, seqs, n, L, name_break);
@@ -1514,8 +1515,17 @@ extern "C" int gm_results_upload(gm_context *c, const gm_hit *hits, const uint32
 extern "C" int gm_results_clear(gm_context *c) {
   if (int r = check_ctx(c)) return r;
   if (int r = ensure_query_state(c)) return r;
+  if (c->async_open) {     // enqueued chunks still merge into the lists: finish them (their result is dropped)
+    GM_CUDA(cudaStreamSynchronize(c->stream));
+    GM_CUDA(cudaMemsetAsync(c->async_ctr.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    GM_CUDA(cudaMemsetAsync(c->async_flag.p, 0, 4 * sizeof(uint32_t), c->stream));
+    c->async_open = 0;
+    c->traced_async = c->dl_open = false;
+  }
   GM_CUDA(cudaMemsetAsync(c->hit_cnt[c->cur_hits].p, 0, (size_t)c->n_queries * 4, c->stream));
   GM_CUDA(cudaStreamSynchronize(c->stream));
+  c->chunks_since_upload.clear();     // the lists are empty again: nothing to redo
+  c->pending = false;
   return 0;
 }
 

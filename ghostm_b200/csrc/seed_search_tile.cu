@@ -626,6 +626,10 @@ cudaError_t seed_search_tile_launch(SearchParams p, const TileGeometry &g, int s
   GM_TILE_CASE(12, 2)
   GM_TILE_CASE(20, 2)
   GM_TILE_CASE(10, 3)
+  GM_TILE_CASE(9, 3)
+  GM_TILE_CASE(11, 3)
+  GM_TILE_CASE(7, 4)
+  GM_TILE_CASE(9, 4)
   GM_TILE_CASE(8, 4)
   GM_TILE_CASE(6, 5)
   GM_TILE_CASE(6, 6)
