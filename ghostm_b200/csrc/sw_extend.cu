@@ -22,6 +22,8 @@
 //  * scores fit s16: the host refuses option sets where L * max(matrix) could overflow.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "gm_common.cuh"
 
 namespace gm {
@@ -268,8 +270,8 @@ __global__ void __launch_bounds__(kSwThreads, 2) sw_extend_pair_kernel(const SwP
 #pragma unroll 4
       for (int k = 0; k < 2 * RH; ++k) {
         const uint32_t row = strip * (2 * RH) + k;
-        int v = -16384 - go;  // padding rows below the query never score
-        if (row < L) v = (int)matT[(int)query[row] * 32 + lane] - go;
+        int v = -16384 - go;  // padding rows below the query, and the SEQUENCE_END column, never score
+        if (row < L && lane != kSeqEnd) v = (int)matT[(int)query[row] * 32 + lane] - go;
         prof[(k < RH ? k : k - RH + kOddRow) * 32 + lane] = (uint16_t)v;
       }
       __syncwarp();
@@ -305,33 +307,40 @@ __global__ void __launch_bounds__(kSwThreads, 2) sw_extend_pair_kernel(const SwP
         }
         uint32_t cmax = 0x80008000u;
         const uint16_t *ta = myprof + ca, *tb = myprof + cb;
-        e[0] = __viaddmax_s16x2(e[0], ge_pk, hgo[0]);                    // aligner.cpp:623-627
-        uint32_t m = __viaddmax_s16x2_relu(                               // :617-620,:629-631
-            top_prev, (uint32_t)tb[0] * 65536u + (uint32_t)ta[0], e[0]);
-#pragma unroll
-        for (int k = 0; k < RH; ++k) {
-          uint32_t m_next = 0;
-          if (k + 1 < RH) {
-            const uint32_t s = (uint32_t)tb[(k + 1) * 32] * 65536u + (uint32_t)ta[(k + 1) * 32];
-            e[k + 1] = __viaddmax_s16x2(e[k + 1], ge_pk, hgo[k + 1]);
-            m_next = __viaddmax_s16x2_relu(hgo[k], s, e[k + 1]);
-          }
-          const uint32_t mgo = __vadd2(m, go_pk);
-          hgo[k] = __viaddmax_s16x2(f, go_pk, mgo);                      // H = max(m, F)  :641-643
-          f = __viaddmax_s16x2(f, gef_pk, mgo);                          // :634-639
-          cmax = __vmaxs2(cmax, hgo[k]);
-          m = m_next;
-        }
         const bool xa = ca == kSeqEnd, xb = cb == kSeqEnd;
-        if (__any_sync(kFull, xa | xb)) {                                // aligner.cpp:664-669
-          const uint32_t keep = (xa ? 0u : 0x0000FFFFu) | (xb ? 0u : 0xFFFF0000u);
-          const uint32_t rst = go_pk & ~keep;
+        const uint32_t keep = (xa ? 0u : 0x0000FFFFu) | (xb ? 0u : 0xFFFF0000u);
+        // One column.  END_COL: a half whose db residue is SEQUENCE_END (aligner.cpp:664-669: both
+        // columns reset to 0, the running maximum survives).  Its profile row is -16384 - open, so
+        // the diagonal term is dead; with E masked to 0 BEFORE it is used, m = 0, F stays below
+        // open and H + open comes out as `open` by itself: the reset costs one LOP3 per row inside
+        // the column instead of two after it.
+        auto column = [&](auto end_col) {
+          constexpr bool END_COL = decltype(end_col)::value;
+          e[0] = __viaddmax_s16x2(e[0], ge_pk, hgo[0]);                  // aligner.cpp:623-627
+          if (END_COL) e[0] &= keep;
+          uint32_t m = __viaddmax_s16x2_relu(                             // :617-620,:629-631
+              top_prev, (uint32_t)tb[0] * 65536u + (uint32_t)ta[0], e[0]);
 #pragma unroll
           for (int k = 0; k < RH; ++k) {
-            hgo[k] = (hgo[k] & keep) | rst;
-            e[k] &= keep;
+            uint32_t m_next = 0;
+            if (k + 1 < RH) {
+              const uint32_t s = (uint32_t)tb[(k + 1) * 32] * 65536u + (uint32_t)ta[(k + 1) * 32];
+              e[k + 1] = __viaddmax_s16x2(e[k + 1], ge_pk, hgo[k + 1]);
+              if (END_COL) e[k + 1] &= keep;
+              m_next = __viaddmax_s16x2_relu(hgo[k], s, e[k + 1]);
+            }
+            const uint32_t mgo = __vadd2(m, go_pk);
+            hgo[k] = __viaddmax_s16x2(f, go_pk, mgo);                    // H = max(m, F)  :641-643
+            f = __viaddmax_s16x2(f, gef_pk, mgo);                        // :634-639
+            cmax = __vmaxs2(cmax, hgo[k]);
+            m = m_next;
           }
-          cmax = (cmax & keep) | (0x80008000u & ~keep);
+        };
+        if (__any_sync(kFull, xa | xb)) {
+          column(std::true_type());
+          cmax = (cmax & keep) | (0x80008000u & ~keep);                  // an END column never holds the maximum
+        } else {
+          column(std::false_type());
         }
         top_prev = top;
         send_top = hgo[RH - 1];
