@@ -323,9 +323,7 @@ std::vector<Segment> front_chunk(gm_context *ctx, uint32_t chunk, uint32_t n_que
 struct Shard {            // one device of a multi-device run
   gm_context *front = nullptr, *back = nullptr;
   uint64_t capacity = 0;
-  gm_stats stats;
   std::mutex front_mu;    // gm_candidates_transfer is serialised per sending context
-  std::vector<Segment> segs;
   std::string error;
 };
 
