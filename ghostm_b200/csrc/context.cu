@@ -315,7 +315,7 @@ struct gm_context {
   bool search_bucket = true; // bucket kernel (threshold 2) in front of it
   bool search_hash = false;  // hash kernel (threshold 2) instead of the bucket kernel: variant 3 only
   bool search_tile = true;   // tile kernel (threshold 2) in front of all of them: variant 4, the default
-  int tile_test = 0;         // variants 5, 6: the tile kernel's dense / in-place paths forced (tests)
+  int tile_test = 0;         // variant 6: the tile kernel's in-place path forced by a tiny staging area (tests)
   bool traceback_fast = true;
   bool deferred = true;      // TraceBack only for the survivors (gm_traceback_pending)
   bool pending = false;      // some resident hit list may hold untraced hits
@@ -1139,7 +1139,7 @@ extern "C" int gm_set_search_variant(gm_context *c, int fast) {
   c->search_bucket = fast >= 2;
   c->search_hash = fast == 3;
   c->search_tile = fast >= 4;
-  c->tile_test = fast >= 5 ? fast - 4 : 0;   // 5: dense mode forced; 6: and a 16-entry staging area
+  c->tile_test = fast >= 5 ? fast - 4 : 0;   // 6: a 16-entry staging area (5 is the same as 4)
   c->traceback_fast = fast != 0;
   return 0;
 }

@@ -212,8 +212,9 @@ int gm_set_deferred_traceback(gm_context *ctx, int on);
  * 3 = hash seed-search kernel under the same conditions (an independent algorithm, ~20 % slower);
  * 1 = balanced register-resident sweep kernel whenever list_len <= 64 and register-resident
  * TraceBack whenever L <= 80, else the generic kernels; 0 = always the generic kernels (tests).
- * 5, 6 = variant 4 with its rare paths forced (5: dense mode, 6: dense mode writing in place), for
- * tests.  All variants produce identical candidates. */
+ * 5 = as 4; 6 = variant 4 with a 16-entry staging area, so that every query takes the rare
+ * "count first, then write straight into the output" path (tests).  All variants produce identical
+ * candidates. */
 int gm_set_search_variant(gm_context *ctx, int variant);
 int gm_traceback_pending(gm_context *ctx, uint64_t *n_done, gm_stats *stats);
 /* Empty the device hit lists without re-uploading the queries. */
